@@ -1,0 +1,129 @@
+/* mlmultipoles.h -- C ABI of libmlmultipoles.so (B200 / sm_100a, FP64).
+ *
+ * Drop-in boundary for the one hot path of ArnaudCassan/microlensing: the Cassan (2017)
+ * binary-lens point-source (A0), quadrupole (A2) and hexadecapole (A4) magnifications of
+ * microlensing/multipoles/multipoles.py.  The reference has no FFI; its boundary is the
+ * Python function surface of that module.  Each entry point below names
+ * the reference interface it replaces (file:line under /root/reference).  The Python side
+ * (microlensing_b200/_capi.py, ctypes) is the only caller in this repo; INTEGRATION.md
+ * shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; complex numbers are interleaved (re, im) doubles;
+ *  - every function returns 0 on success, a negative MLM_E* code for argument errors, or a
+ *    positive cudaError_t; mlm_last_error() gives the message; nothing throws;
+ *  - the caller owns every buffer.  Un-suffixed functions take DEVICE pointers and enqueue
+ *    on `stream` (a cudaStream_t passed as void*, NULL = the context's own stream) without
+ *    synchronising; *_host functions take HOST pointers, copy in/out themselves and return
+ *    when the results are in the host buffers;
+ *  - frames: `zeta` arguments are in the PRIMARY-LENS frame (primary mass 1/(1+q) at 0,
+ *    secondary q/(1+q) at -s), exactly what _solvelenseq receives (multipoles.py:156);
+ *    map/light-curve generators take CENTRE-OF-MASS coordinates and apply
+ *    zeta = zeta_cm - s q/(1+q) themselves (multipoles.py:177-178);
+ *  - order = 2 computes A0, A2 (quadrupole, multipoles.py:12-65; A4 output is set to 0),
+ *    order = 4 computes A0, A2, A4 (hexadecapole, multipoles.py:67-148);
+ *  - nimg / flags outputs may be NULL.
+ * There is no CPU fallback anywhere in the library: without a CUDA device mlm_create fails.
+ */
+#ifndef MLMULTIPOLES_H
+#define MLMULTIPOLES_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mlm_context mlm_context;
+
+/* argument-error codes (negative; CUDA errors are returned as positive cudaError_t) */
+#define MLM_OK 0
+#define MLM_EINVAL (-1)   /* bad argument (NULL pointer, order not 2/4, negative size, s<=0, q<=0) */
+#define MLM_ENOMEM (-2)   /* host allocation failed */
+
+/* per-position flag bits written to `flags` (the reference flags nothing) */
+#define MLM_FLAG_NOCONV 1    /* a root-finder iteration cap was hit */
+#define MLM_FLAG_VIETE 2     /* reserved: sum-of-roots check failed */
+#define MLM_FLAG_NEARCRIT 4  /* min over images of |1-|W2|^2| < 1e-3 (near a critical curve) */
+#define MLM_FLAG_AMBIG 8     /* a root's lens-equation residual within a decade of 1e-6 (multipoles.py:183) */
+#define MLM_FLAG_SERIES 16   /* |A4-A2| > |A2-A0|: multipole series not converging */
+#define MLM_FLAG_DEGEN 32    /* leading polynomial coefficient exactly 0 (zeta = 0 or zeta = -s) */
+
+/* ---- context --------------------------------------------------------------------------- */
+int mlm_create(int device, mlm_context** out);
+int mlm_destroy(mlm_context* ctx);
+const char* mlm_last_error(mlm_context* ctx);          /* ctx may be NULL: last global error */
+const char* mlm_version(void);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int mlm_launch_count(mlm_context* ctx, int64_t* out);
+int mlm_synchronize(mlm_context* ctx);
+/* pinned host memory for *_host outputs (so the D2H copies overlap with the kernels) */
+int mlm_alloc_host(mlm_context* ctx, int64_t bytes, void** out);
+int mlm_free_host(mlm_context* ctx, void* p);
+
+/* ---- the fused path: replaces the per-position body of example(), multipoles.py:181-202
+ *      (_solvelenseq :156-165, selection :182-183, Wk :185-201, hexadecapole :67-148) -------- */
+
+/* N arbitrary source positions, one (s,q,rho,Gamma).  zeta: n complex (primary frame). */
+int mlm_points(mlm_context* ctx, double s, double q, double rho, double Gamma,
+               const double* zeta, int64_t n, int order,
+               double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags, void* stream);
+int mlm_points_host(mlm_context* ctx, double s, double q, double rho, double Gamma,
+                    const double* zeta, int64_t n, int order,
+                    double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags);
+
+/* Magnification map: pixel (row r, column c) has centre-of-mass source position
+ *   x = x0 + (c + 0.5) dx,  y = y0 + (r + 0.5) dy          (generated in the kernel),
+ * rows [row0, row0 + nrows) of an nx-wide map are written to out[(r - row0) * nx + c]
+ * (row-shardable: "... to be computed for all source center positions", multipoles.py:184). */
+int mlm_map(mlm_context* ctx, double s, double q, double rho, double Gamma,
+            double x0, double y0, double dx, double dy, int64_t nx, int64_t row0, int64_t nrows, int order,
+            double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags, void* stream);
+int mlm_map_host(mlm_context* ctx, double s, double q, double rho, double Gamma,
+                 double x0, double y0, double dx, double dy, int64_t nx, int64_t row0, int64_t nrows, int order,
+                 double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags);
+
+/* Batched model grid: M models x T epochs.  Model m has (s,q,rho,Gamma,u0,alpha)[m] (device
+ * arrays of length M); epoch t has tau = tau0 + t dtau; centre-of-mass source position
+ * zeta_cm = (tau + i u0) exp(i alpha).  Outputs are [m * T + t]. */
+int mlm_models(mlm_context* ctx, const double* s, const double* q, const double* rho, const double* Gamma,
+               const double* u0, const double* alpha, int64_t M, double tau0, double dtau, int64_t T, int order,
+               double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags, void* stream);
+int mlm_models_host(mlm_context* ctx, const double* s, const double* q, const double* rho, const double* Gamma,
+                    const double* u0, const double* alpha, int64_t M, double tau0, double dtau, int64_t T, int order,
+                    double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags);
+
+/* ---- drop-ins for the individual reference functions ------------------------------------ */
+
+/* quadrupole(Wk,rho,Gamma) multipoles.py:12 (order 2, out = [A0,A2]) and
+ * hexadecapole(Wk,rho,Gamma) multipoles.py:67 (order 4, out = [A0,A2,A4]).
+ * Wk: the reference's (7, n) complex128 C-ordered table, rows 2..(order==2 ? 4 : 6) are read,
+ * rows 0-1 never (np.empty garbage in the reference, multipoles.py:186).  Sums over all n. */
+int mlm_from_wk(mlm_context* ctx, const double* Wk, int64_t n, int order, double rho, double Gamma,
+                double* out, void* stream);
+int mlm_from_wk_host(mlm_context* ctx, const double* Wk, int64_t n, int order, double rho, double Gamma,
+                     double* out);
+
+/* _solvelenseq(s,q,zeta) multipoles.py:156: all roots of the lens polynomial, 5 complex per
+ * position (NaN where np.roots would return fewer: zeta = 0, zeta = -s), order unspecified. */
+int mlm_solve(mlm_context* ctx, double s, double q, const double* zeta, int64_t n, double* roots, void* stream);
+int mlm_solve_host(mlm_context* ctx, double s, double q, const double* zeta, int64_t n, double* roots);
+
+/* _akl(mu,W2,Qkl) multipoles.py:150: out = mu (conj(Q) + conj(W2) Q), elementwise; all four
+ * arrays are n complex numbers (a real mu is passed with zero imaginary parts). */
+int mlm_akl(mlm_context* ctx, const double* mu, const double* W2, const double* Q, int64_t n, double* out,
+            void* stream);
+int mlm_akl_host(mlm_context* ctx, const double* mu, const double* W2, const double* Q, int64_t n, double* out);
+
+/* ---- measurement helpers ----------------------------------------------------------------- */
+/* DFMA-chain microbenchmark: measured FP64 FMA throughput of this GPU in TFLOP/s
+ * (2 flop per DFMA), the denominator of the FP64 roofline (MEASURED_PEAKS.json has none). */
+int mlm_fp64_peak(mlm_context* ctx, double* tflops);
+/* static description of the fused kernel (registers per thread, spill bytes) from
+ * cudaFuncGetAttributes: [0]=regs points<4>, [1]=local bytes points<4>, [2]=regs map<4>, [3]=local bytes map<4> */
+int mlm_kernel_info(mlm_context* ctx, int32_t* out, int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MLMULTIPOLES_H */

@@ -1,0 +1,163 @@
+"""ctypes binding of libmlmultipoles.so (the C ABI declared in include/mlmultipoles.h).
+
+There is no CPU fallback: if the CUDA library is missing or no CUDA device is present,
+every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+import weakref
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmlmultipoles.so")
+
+c_double_p = ctypes.POINTER(ctypes.c_double)
+c_u8_p = ctypes.POINTER(ctypes.c_uint8)
+_D, _I, _L, _P = ctypes.c_double, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p
+
+# name -> argument types (all return int unless noted); mirrors include/mlmultipoles.h
+SIGNATURES = {
+    "mlm_create": [_I, ctypes.POINTER(_P)],
+    "mlm_destroy": [_P],
+    "mlm_launch_count": [_P, ctypes.POINTER(_L)],
+    "mlm_synchronize": [_P],
+    "mlm_alloc_host": [_P, _L, ctypes.POINTER(_P)],
+    "mlm_free_host": [_P, _P],
+    "mlm_points": [_P, _D, _D, _D, _D, _P, _L, _I, _P, _P, _P, _P, _P, _P],
+    "mlm_points_host": [_P, _D, _D, _D, _D, _P, _L, _I, _P, _P, _P, _P, _P],
+    "mlm_map": [_P, _D, _D, _D, _D, _D, _D, _D, _D, _L, _L, _L, _I, _P, _P, _P, _P, _P, _P],
+    "mlm_map_host": [_P, _D, _D, _D, _D, _D, _D, _D, _D, _L, _L, _L, _I, _P, _P, _P, _P, _P],
+    "mlm_models": [_P, _P, _P, _P, _P, _P, _P, _L, _D, _D, _L, _I, _P, _P, _P, _P, _P, _P],
+    "mlm_models_host": [_P, _P, _P, _P, _P, _P, _P, _L, _D, _D, _L, _I, _P, _P, _P, _P, _P],
+    "mlm_from_wk": [_P, _P, _L, _I, _D, _D, _P, _P],
+    "mlm_from_wk_host": [_P, _P, _L, _I, _D, _D, _P],
+    "mlm_solve": [_P, _D, _D, _P, _L, _P, _P],
+    "mlm_solve_host": [_P, _D, _D, _P, _L, _P],
+    "mlm_akl": [_P, _P, _P, _P, _L, _P, _P],
+    "mlm_akl_host": [_P, _P, _P, _P, _L, _P],
+    "mlm_fp64_peak": [_P, ctypes.POINTER(_D)],
+    "mlm_kernel_info": [_P, ctypes.POINTER(ctypes.c_int32), _I],
+}
+STRING_FUNCS = {"mlm_last_error": [_P], "mlm_version": []}
+
+_lib = None
+_lock = threading.Lock()
+_contexts: dict = {}
+
+
+class MlmError(RuntimeError):
+    pass
+
+
+def load_library():
+    """dlopen libmlmultipoles.so and declare every prototype.  Raises if it is not built."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is not built. Run `python -m microlensing_b200.build` (needs nvcc). "
+                "microlensing_b200 has no CPU fallback.")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = argtypes
+            fn.restype = ctypes.c_int
+        for name, argtypes in STRING_FUNCS.items():
+            fn = getattr(lib, name)
+            fn.argtypes = argtypes
+            fn.restype = ctypes.c_char_p
+        _lib = lib
+        return lib
+
+
+class Context:
+    """One mlm_context (device, two streams, scratch) per (process, device)."""
+
+    def __init__(self, device: int):
+        self.lib = load_library()
+        self.device = device
+        h = _P()
+        rc = self.lib.mlm_create(device, ctypes.byref(h))
+        if rc != 0:
+            msg = self.lib.mlm_last_error(None).decode()
+            raise MlmError(f"mlm_create(device={device}) failed ({rc}): {msg} -- a CUDA device is required, "
+                           "there is no CPU fallback")
+        self.handle = h
+        self._finalizer = weakref.finalize(self, self.lib.mlm_destroy, h)
+
+    def check(self, rc: int, what: str):
+        if rc != 0:
+            msg = self.lib.mlm_last_error(self.handle).decode()
+            if rc < 0:
+                raise ValueError(f"{what}: {msg}")
+            raise MlmError(f"{what} failed (cudaError {rc}): {msg}")
+
+    def launch_count(self) -> int:
+        n = _L(0)
+        self.check(self.lib.mlm_launch_count(self.handle, ctypes.byref(n)), "mlm_launch_count")
+        return int(n.value)
+
+    def synchronize(self):
+        self.check(self.lib.mlm_synchronize(self.handle), "mlm_synchronize")
+
+    def fp64_peak_tflops(self) -> float:
+        v = _D(0.0)
+        self.check(self.lib.mlm_fp64_peak(self.handle, ctypes.byref(v)), "mlm_fp64_peak")
+        return float(v.value)
+
+    def kernel_info(self) -> dict:
+        a = (ctypes.c_int32 * 4)()
+        self.check(self.lib.mlm_kernel_info(self.handle, a, 4), "mlm_kernel_info")
+        return {"k_points4_regs": a[0], "k_points4_local_bytes": a[1], "k_map4_regs": a[2], "k_map4_local_bytes": a[3]}
+
+    def pinned_empty(self, shape, dtype) -> np.ndarray:
+        """numpy array over page-locked host memory (freed when the array and its views die)."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) if np.ndim(shape) else int(shape)
+        nbytes = max(n * dtype.itemsize, 1)
+        p = _P()
+        self.check(self.lib.mlm_alloc_host(self.handle, nbytes, ctypes.byref(p)), "mlm_alloc_host")
+        buf = (ctypes.c_char * nbytes).from_address(p.value)
+        weakref.finalize(buf, self.lib.mlm_free_host, self.handle, p)
+        return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+
+
+def default_device() -> int:
+    for key in ("MLM_DEVICE", "LOCAL_RANK"):
+        if key in os.environ:
+            return int(os.environ[key])
+    return 0
+
+
+def context(device: int | None = None) -> Context:
+    if device is None:
+        device = default_device()
+    with _lock:
+        ctx = _contexts.get(device)
+    if ctx is None:
+        ctx = Context(device)
+        with _lock:
+            _contexts.setdefault(device, ctx)
+            ctx = _contexts[device]
+    return ctx
+
+
+def ptr(a) -> _P:
+    """Address of a C-contiguous numpy array, a raw int device pointer, or None."""
+    if a is None:
+        return _P(None)
+    if isinstance(a, np.ndarray):
+        if not a.flags.c_contiguous:
+            raise ValueError("array must be C-contiguous")
+        return _P(a.ctypes.data)
+    if isinstance(a, int):
+        return _P(a)
+    if hasattr(a, "data_ptr"):          # torch tensor (device or host); plumbing only
+        return _P(a.data_ptr())
+    raise TypeError(f"cannot take the address of {type(a)}")

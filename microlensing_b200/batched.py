@@ -1,0 +1,136 @@
+"""Batched entry points (NEW API: the reference has only an implied Python loop,
+"... to be computed for all source center positions", multipoles.py:184).
+
+Every function takes HOST data (numpy), calls the CUDA library through the C ABI
+(`*_host` entry points: the host<->device copies happen inside the call, chunked and
+overlapped with the kernels) and returns numpy arrays.  `*_device` variants take device
+pointers (e.g. torch tensors' data_ptr()) and only enqueue work on a stream.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _capi
+
+__all__ = ["Magnification", "magnification_points", "magnification_map", "magnification_models",
+           "map_coordinates", "lightcurve_coordinates", "alloc_outputs", "map_device", "points_device",
+           "models_device"]
+
+
+class Magnification(dict):
+    """dict with keys A0, A2, A4 (float64), nimg, flags (uint8); attribute access too."""
+    __getattr__ = dict.__getitem__
+
+
+def alloc_outputs(shape, device=None, pinned=True) -> Magnification:
+    """Output buffers (page-locked by default so D2H overlaps with compute)."""
+    ctx = _capi.context(device)
+    mk = (lambda dt: ctx.pinned_empty(shape, dt)) if pinned else (lambda dt: np.empty(shape, dt))
+    return Magnification(A0=mk(np.float64), A2=mk(np.float64), A4=mk(np.float64),
+                         nimg=mk(np.uint8), flags=mk(np.uint8))
+
+
+def _check_out(out, shape):
+    for k, dt in (("A0", np.float64), ("A2", np.float64), ("A4", np.float64), ("nimg", np.uint8), ("flags", np.uint8)):
+        a = out[k]
+        if a.shape != tuple(shape) or a.dtype != dt or not a.flags.c_contiguous:
+            raise ValueError(f"out[{k!r}] must be C-contiguous {dt} of shape {tuple(shape)}")
+
+
+def map_coordinates(s, q, x0, y0, dx, dy, nx, ny, row0=0, nrows=None):
+    """Primary-frame zeta of every pixel, bit-identical to what the map kernel generates:
+    x = x0 + (c + 0.5) dx, y = y0 + (r + 0.5) dy (centre of mass), zeta = x - s q/(1+q) + i y
+    (multipoles.py:177-178)."""
+    nrows = ny - row0 if nrows is None else nrows
+    c = np.arange(nx, dtype=np.float64)
+    r = np.arange(row0, row0 + nrows, dtype=np.float64)
+    x = (x0 + (c + 0.5) * dx) + (-(s * q / (1. + q)))
+    y = y0 + (r + 0.5) * dy
+    return x[None, :] + 1j * y[:, None]
+
+
+def lightcurve_coordinates(s, q, u0, alpha, tau0, dtau, T):
+    """Primary-frame zeta of the epochs tau_t = tau0 + t dtau of a straight trajectory,
+    zeta_cm = (tau + i u0) exp(i alpha), same arithmetic as the models kernel."""
+    t = np.arange(T, dtype=np.float64)
+    tau = tau0 + t * dtau
+    ca, sa = np.cos(alpha), np.sin(alpha)
+    zx = (tau * ca + (-(u0 * sa))) + (-(s * q / (1. + q)))
+    zy = tau * sa + u0 * ca
+    return zx + 1j * zy
+
+
+def magnification_points(s, q, rho, Gamma, zeta, order=4, out=None, device=None) -> Magnification:
+    """A0/A2/A4, image count and flags at arbitrary primary-frame positions `zeta` (any shape).
+
+    Per position this is the body of example(), multipoles.py:181-202.
+    """
+    ctx = _capi.context(device)
+    zeta = np.ascontiguousarray(zeta, dtype=np.complex128)
+    shape = zeta.shape
+    if out is None:
+        out = alloc_outputs(shape, device, pinned=zeta.size >= (1 << 16))
+    _check_out(out, shape)
+    ctx.check(ctx.lib.mlm_points_host(ctx.handle, s, q, rho, Gamma, _capi.ptr(zeta), zeta.size, order,
+                                      _capi.ptr(out["A0"]), _capi.ptr(out["A2"]), _capi.ptr(out["A4"]),
+                                      _capi.ptr(out["nimg"]), _capi.ptr(out["flags"])), "mlm_points_host")
+    return out
+
+
+def magnification_map(s, q, rho, Gamma, x0, y0, dx, dy, nx, ny, row0=0, nrows=None, order=4, out=None,
+                      device=None) -> Magnification:
+    """Rows [row0, row0+nrows) of an nx x ny magnification map (centre-of-mass window, pixel-centre
+    sampling); coordinates are generated on the GPU, results land in `out` (nrows, nx)."""
+    ctx = _capi.context(device)
+    nrows = ny - row0 if nrows is None else nrows
+    shape = (nrows, nx)
+    if out is None:
+        out = alloc_outputs(shape, device, pinned=nrows * nx >= (1 << 16))
+    _check_out(out, shape)
+    ctx.check(ctx.lib.mlm_map_host(ctx.handle, s, q, rho, Gamma, x0, y0, dx, dy, nx, row0, nrows, order,
+                                   _capi.ptr(out["A0"]), _capi.ptr(out["A2"]), _capi.ptr(out["A4"]),
+                                   _capi.ptr(out["nimg"]), _capi.ptr(out["flags"])), "mlm_map_host")
+    return out
+
+
+def magnification_models(s, q, rho, Gamma, u0, alpha, tau0, dtau, T, order=4, out=None, device=None) -> Magnification:
+    """Batched fit grid: M models (arrays s, q, rho, Gamma, u0, alpha of length M) x T epochs."""
+    ctx = _capi.context(device)
+    arrs = [np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float64), np.shape(s)))
+            for a in (s, q, rho, Gamma, u0, alpha)]
+    M = arrs[0].size
+    if not (np.all(arrs[0] > 0) and np.all(arrs[1] > 0)):
+        raise ValueError("magnification_models: s and q must be positive")
+    shape = (M, T)
+    if out is None:
+        out = alloc_outputs(shape, device, pinned=M * T >= (1 << 16))
+    _check_out(out, shape)
+    ctx.check(ctx.lib.mlm_models_host(ctx.handle, *[_capi.ptr(a) for a in arrs], M, tau0, dtau, T, order,
+                                      _capi.ptr(out["A0"]), _capi.ptr(out["A2"]), _capi.ptr(out["A4"]),
+                                      _capi.ptr(out["nimg"]), _capi.ptr(out["flags"])), "mlm_models_host")
+    return out
+
+
+# ---- device-pointer variants (enqueue only; buffers e.g. torch CUDA tensors) -----------------
+def _p(x):
+    return _capi.ptr(x)
+
+
+def points_device(s, q, rho, Gamma, zeta, n, A0, A2, A4, nimg=None, flags=None, order=4, stream=None, device=None):
+    ctx = _capi.context(device)
+    ctx.check(ctx.lib.mlm_points(ctx.handle, s, q, rho, Gamma, _p(zeta), n, order, _p(A0), _p(A2), _p(A4),
+                                 _p(nimg), _p(flags), _p(stream)), "mlm_points")
+
+
+def map_device(s, q, rho, Gamma, x0, y0, dx, dy, nx, row0, nrows, A0, A2, A4, nimg=None, flags=None, order=4,
+               stream=None, device=None):
+    ctx = _capi.context(device)
+    ctx.check(ctx.lib.mlm_map(ctx.handle, s, q, rho, Gamma, x0, y0, dx, dy, nx, row0, nrows, order,
+                              _p(A0), _p(A2), _p(A4), _p(nimg), _p(flags), _p(stream)), "mlm_map")
+
+
+def models_device(s, q, rho, Gamma, u0, alpha, M, tau0, dtau, T, A0, A2, A4, nimg=None, flags=None, order=4,
+                  stream=None, device=None):
+    ctx = _capi.context(device)
+    ctx.check(ctx.lib.mlm_models(ctx.handle, _p(s), _p(q), _p(rho), _p(Gamma), _p(u0), _p(alpha), M, tau0, dtau, T,
+                                 order, _p(A0), _p(A2), _p(A4), _p(nimg), _p(flags), _p(stream)), "mlm_models")

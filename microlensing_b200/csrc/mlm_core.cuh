@@ -1,0 +1,550 @@
+// mlm_core.cuh -- per-source-position arithmetic of the binary-lens A0/A2/A4 path.
+//
+// Everything here runs in registers of ONE thread (one source position):
+//   (a) lens polynomial from (s, q, zeta)        reference: multipoles.py:159-164
+//   (b) all complex roots (Laguerre + deflation, Newton polish)   replaces np.roots, multipoles.py:165
+//   (c) physical images by the residual test     reference: multipoles.py:182-183
+//   (d) W_2..W_6 per image                        reference: multipoles.py:197-201
+//   (e) mu0, mu2, mu4 per image and the sums      reference: multipoles.py:91-146
+//
+// (e) is NOT a transcription of the reference's (xi, eta) recursion.  It works in the
+// Wirtinger basis (d/dzeta, d/dzetabar), scaled so that dzbar/dzetabar = 1, where
+//   * only 14 of the 20 Taylor coefficients up to order 5 are needed,
+//   * the order-5 contribution collapses to Re(R32) ("Wirtinger form"),
+//   * mu2 = mu0^4 * lap1, mu4 = 2 * mu0^6 * lap2.
+// tests/ verifies it against the oracle's literal restatement of the reference formulae.
+//
+// The functions are __host__ __device__ so that tests/ can compile them with g++ into a
+// test-only checker of the kernel logic (tests/host_emu); the product only ever calls them
+// from CUDA kernels (mlm_kernels.cu).
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define MLM_HD __host__ __device__ __forceinline__
+#define MLM_HDI __host__ __device__ inline
+#else
+#define MLM_HD inline __attribute__((always_inline))
+#define MLM_HDI inline
+#endif
+
+namespace mlm {
+
+// ---------------------------------------------------------------------------------------
+// complex double in two registers
+// ---------------------------------------------------------------------------------------
+struct cd {
+    double x, y;
+};
+
+MLM_HD cd mk(double x, double y) { cd r; r.x = x; r.y = y; return r; }
+MLM_HD cd operator+(cd a, cd b) { return mk(a.x + b.x, a.y + b.y); }
+MLM_HD cd operator-(cd a, cd b) { return mk(a.x - b.x, a.y - b.y); }
+MLM_HD cd operator-(cd a) { return mk(-a.x, -a.y); }
+MLM_HD cd conj(cd a) { return mk(a.x, -a.y); }
+MLM_HD cd scale(double s, cd a) { return mk(s * a.x, s * a.y); }
+MLM_HD double norm2(cd a) { return fma(a.x, a.x, a.y * a.y); }
+// a*b
+MLM_HD cd cmul(cd a, cd b) { return mk(fma(a.x, b.x, -(a.y * b.y)), fma(a.x, b.y, a.y * b.x)); }
+// a*a
+MLM_HD cd csq(cd a) { return mk(fma(a.x, a.x, -(a.y * a.y)), 2.0 * (a.x * a.y)); }
+// a*b + c
+MLM_HD cd cfma(cd a, cd b, cd c) {
+    return mk(fma(a.x, b.x, fma(-a.y, b.y, c.x)), fma(a.x, b.y, fma(a.y, b.x, c.y)));
+}
+// conj(a)*b + c
+MLM_HD cd cjfma(cd a, cd b, cd c) {
+    return mk(fma(a.x, b.x, fma(a.y, b.y, c.x)), fma(a.x, b.y, fma(-a.y, b.x, c.y)));
+}
+// s*a + c (real s)
+MLM_HD cd rfma(double s, cd a, cd c) { return mk(fma(s, a.x, c.x), fma(s, a.y, c.y)); }
+// Re(a*b), Re(a*conj(b))
+MLM_HD double re_mul(cd a, cd b) { return fma(a.x, b.x, -(a.y * b.y)); }
+MLM_HD double re_mulc(cd a, cd b) { return fma(a.x, b.x, a.y * b.y); }
+
+// ---------------------------------------------------------------------------------------
+// fast FP64 reciprocal / reciprocal square root.
+// On the device: MUFU.RCP64H / MUFU.RSQ64H seed (rcp.approx.ftz.f64, ~2^-20 relative) and
+// two Newton steps on the FP64 pipe; no special-case branch (0 -> NaN/inf, which the callers
+// rely on: a root at a lens position must yield a NaN residual exactly like 1/0 in NumPy).
+// ---------------------------------------------------------------------------------------
+MLM_HD double rcp(double a) {
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    double e = fma(-a, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-a, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+#else
+    return 1.0 / a;
+#endif
+}
+
+MLM_HD double rsqrt_(double a) {
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    // Newton for 1/sqrt(a): r <- r + r*(1 - a r^2)/2
+    double h = 0.5 * r;
+    double e = fma(-a * r, r, 1.0);
+    r = fma(h, e, r);
+    h = 0.5 * r;
+    e = fma(-a * r, r, 1.0);
+    r = fma(h, e, r);
+    return r;
+#else
+    return 1.0 / sqrt(a);
+#endif
+}
+
+// 1/a (complex)
+MLM_HD cd crcp(cd a) {
+    double r = rcp(norm2(a));
+    return mk(a.x * r, -(a.y * r));
+}
+
+// principal square root of a complex number (2 rsqrt, no division)
+MLM_HD cd csqrt_(cd a) {
+    double n2 = norm2(a);
+    if (!(n2 > 0.0)) return mk(0.0, 0.0);            // 0 (or NaN -> 0, caller copes)
+    double r = n2 * rsqrt_(n2);                       // |a|
+    double h = 0.5 * (r + fabs(a.x));                 // >= |a|/2 > 0
+    double rs = rsqrt_(h);
+    double t = h * rs;                                // sqrt(h)
+    double u = 0.5 * a.y * rs;                        // a.y / (2 sqrt(h))
+    return (a.x >= 0.0) ? mk(t, u) : mk(fabs(u), (a.y >= 0.0) ? t : -t);
+}
+
+// ---------------------------------------------------------------------------------------
+// per-(s,q) table (kernel parameter -> constant bank; built on the host by mlm_make_table)
+// ---------------------------------------------------------------------------------------
+struct LensTable {
+    double s, q;
+    double m2;                                        // (1+q)^2
+    double k40, k41, k42, k43;
+    double k30, k31, k32, k33, k34, k35;
+    double k20, k21, k22, k23, k24;
+    double k10, k11, k12;
+    double k00;
+    double alpha[7];                                  // W_k = alpha_k z^-k + beta_k (z+s)^-k, k=1..6
+    double beta[7];
+};
+
+MLM_HDI void make_table(double s, double q, LensTable* t) {
+    const double m = 1.0 + q, s2 = s * s, s3 = s2 * s, m2 = m * m;
+    t->s = s; t->q = q; t->m2 = m2;
+    t->k40 = m * s * q; t->k41 = -m2 * s; t->k42 = 1.0 + 2.0 * s2; t->k43 = 2.0 * s;
+    t->k30 = m * s2 * q; t->k31 = -s * m2; t->k32 = m * (2.0 * s + s3 * m); t->k33 = m2 * s2;
+    t->k34 = -2.0 * m2 * (1.0 + s2); t->k35 = -2.0 * m2 * s;
+    t->k20 = -m * s * q; t->k21 = -m * s2 * (q - 1.0); t->k22 = -m * (m + s2 * (2.0 + q));
+    t->k23 = -m * (2.0 * s * (2.0 + q) + s3 * m); t->k24 = -m2 * s2;
+    t->k10 = -s * m * (2.0 + s2); t->k11 = -2.0 * s2 * m; t->k12 = -s2 * q;
+    t->k00 = -s2;
+    double f = 1.0;
+    t->alpha[0] = t->beta[0] = 0.0;
+    for (int k = 1; k <= 6; ++k) {
+        if (k > 1) f *= -(double)(k - 1);             // 1, -1, 2, -6, 24, -120
+        t->alpha[k] = f / m;
+        t->beta[k] = f * q / m;
+    }
+}
+
+// (a) coefficients c[k] of z^k, k = 0..5        (multipoles.py:159-164, A.2 of SURVEY.md)
+MLM_HD void lens_polynomial(const LensTable& T, cd zeta, cd c[6]) {
+    const cd zb = conj(zeta);
+    const double n = norm2(zeta);
+    const cd szb = mk(T.s + zb.x, zb.y);
+    c[5] = scale(T.m2, cmul(zb, szb));
+    {   // c4 = k40 + k41 n + m2 zb (k42 - n + k43 zb)
+        cd in = mk(fma(T.k43, zb.x, T.k42 - n), T.k43 * zb.y);
+        cd t = scale(T.m2, cmul(zb, in));
+        c[4] = mk(t.x + fma(T.k41, n, T.k40), t.y);
+    }
+    {   // c3 = k30 + k31 zeta + zb (k32 + k33 zb) + n (k34 + k35 zb)
+        cd in = mk(fma(T.k33, zb.x, T.k32), T.k33 * zb.y);
+        cd t = cmul(zb, in);
+        t = rfma(T.k31, zeta, t);
+        t = rfma(n, mk(fma(T.k35, zb.x, T.k34), T.k35 * zb.y), t);
+        c[3] = mk(t.x + T.k30, t.y);
+    }
+    {   // c2 = k20 + k21 zb + k22 zeta + n (k23 + k24 zb)
+        cd t = scale(T.k21, zb);
+        t = rfma(T.k22, zeta, t);
+        t = rfma(n, mk(fma(T.k24, zb.x, T.k23), T.k24 * zb.y), t);
+        c[2] = mk(t.x + T.k20, t.y);
+    }
+    c[1] = mk(fma(T.k10, zeta.x, fma(T.k11, n, T.k12)), T.k10 * zeta.y);
+    c[0] = scale(T.k00, zeta);
+}
+
+// ---------------------------------------------------------------------------------------
+// (b) root finder
+// ---------------------------------------------------------------------------------------
+#ifndef MLM_COUNT
+#define MLM_COUNT(name)                              /* test-only instrumentation hook */
+#endif
+#define MLM_EPS 1.1102230246251565e-16               /* 2^-53 */
+#define MLM_LAG_MAXIT 64
+#ifndef MLM_FLAG_NOCONV          /* same values as include/mlmultipoles.h */
+#define MLM_FLAG_NOCONV 1        /* an iteration cap was hit */
+#define MLM_FLAG_VIETE 2         /* reserved */
+#define MLM_FLAG_NEARCRIT 4      /* min_i |1-|W2_i|^2| < 1e-3 over the physical images */
+#define MLM_FLAG_AMBIG 8         /* a root residual within a decade of the 1e-6 threshold */
+#define MLM_FLAG_SERIES 16       /* |A4-A2| > |A2-A0| : multipole series not converging */
+#define MLM_FLAG_DEGEN 32        /* degenerate polynomial (leading coefficient exactly 0) */
+#endif
+
+MLM_HD double mag1(cd a) { return fabs(a.x) + fabs(a.y); }   // |a| <= mag1 <= sqrt2 |a|
+
+// p, p' at x for the full quintic
+MLM_HD void horner2(const cd c[6], cd x, cd& p, cd& dp) {
+    p = c[5];
+    dp = mk(0.0, 0.0);
+#pragma unroll
+    for (int k = 4; k >= 0; --k) {
+        dp = cfma(dp, x, p);
+        p = cfma(p, x, c[k]);
+    }
+}
+
+// All roots of c[5] z^5 + ... + c[0].  Returns the degree actually solved (5 unless leading
+// coefficients are exactly zero, as np.roots does); slots >= degree are set to NaN.
+// Laguerre iterations from x=0 on the successively deflated polynomial (kept zero-padded in
+// d[0..5] so one code path serves every degree), closed form for the last two roots, then
+// Newton polishing of every root on the undeflated polynomial.
+MLM_HD int solve_roots(const cd c[6], cd z[5], unsigned& flags) {
+    cd d[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) d[k] = c[k];
+    int deg = 5;
+    if (d[5].x == 0.0 && d[5].y == 0.0) {
+        flags |= MLM_FLAG_DEGEN;
+        deg = 4;
+        if (d[4].x == 0.0 && d[4].y == 0.0) {
+            deg = 3;
+            if (d[3].x == 0.0 && d[3].y == 0.0) deg = 2;   // cannot happen for s>0; keeps the loop bounded
+        }
+    }
+    const int deg0 = deg;
+    const double qnan = nan("");
+#pragma unroll
+    for (int k = 0; k < 5; ++k) z[k] = mk(qnan, qnan);
+
+    cd x = mk(0.0, 0.0);
+    int it = 0;
+    while (deg > 2) {
+        // p (b), p' (dd), p''/2 (f) of the current deflated polynomial at x
+        cd b = d[5], dd = mk(0.0, 0.0), f = mk(0.0, 0.0);
+        const double ax = mag1(x);
+        double E = mag1(d[5]);
+#pragma unroll
+        for (int k = 4; k >= 0; --k) {
+            f = cfma(f, x, dd);
+            dd = cfma(dd, x, b);
+            b = cfma(b, x, d[k]);
+            E = fma(E, ax, mag1(d[k]));
+        }
+        MLM_COUNT(laguerre_evals);
+        const double b2 = norm2(b);
+        const double tol = 16.0 * MLM_EPS * E;
+        bool done = (b2 <= tol * tol);
+        if (!done) {
+            const double m = (double)deg;
+            const cd ib = crcp(b);
+            const cd g = cmul(dd, ib);
+            const cd g2 = csq(g);
+            const cd fb = cmul(f, ib);
+            const cd h = mk(fma(-2.0, fb.x, g2.x), fma(-2.0, fb.y, g2.y));
+            // sq = sqrt((m-1) (m h - g2))
+            const cd rad = scale(m - 1.0, mk(fma(m, h.x, -g2.x), fma(m, h.y, -g2.y)));
+            const cd sq = csqrt_(rad);
+            cd gp = g + sq;
+            const cd gm = g - sq;
+            if (norm2(gp) < norm2(gm)) gp = gm;
+            const double gp2 = norm2(gp);
+            cd dx;
+            if (gp2 > 0.0) {
+                const double r = m * rcp(gp2);
+                dx = mk(gp.x * r, -(gp.y * r));
+            } else {
+                // p' = p'' = 0: leave the stationary point with a kick of size 1+|x| whose
+                // direction changes from one iteration to the next (unit vectors 3-4-5, 5-12-13)
+                const double rr = 1.0 + ax;
+                const double ux = (it & 1) ? 0.6 : -0.38461538461538464;
+                const double uy = (it & 1) ? 0.8 : 0.9230769230769231;
+                dx = (it & 2) ? mk(-rr * uy, rr * ux) : mk(rr * ux, rr * uy);
+            }
+            ++it;
+            // break rare limit cycles with a fractional step every 10th iteration
+            if (it % 10 == 0) dx = scale(0.37 + 0.061 * (double)(it / 10), dx);
+            x = x - dx;
+            // cubic convergence: once the step is below 1e-7 |x| the new x is at rounding level
+            const double x2 = norm2(x);
+            done = (norm2(dx) <= 1e-14 * x2) || (it >= MLM_LAG_MAXIT);
+            if (it >= MLM_LAG_MAXIT) flags |= MLM_FLAG_NOCONV;
+        }
+        if (done) {
+#pragma unroll
+            for (int k = 2; k < 5; ++k)
+                if (k == deg - 1) z[k] = x;
+            // forward deflation by (z - x), zero-padded: d <- quotient
+            cd q4 = d[5];
+            cd q3 = cfma(q4, x, d[4]);
+            cd q2 = cfma(q3, x, d[3]);
+            cd q1 = cfma(q2, x, d[2]);
+            cd q0 = cfma(q1, x, d[1]);
+            d[5] = mk(0.0, 0.0); d[4] = q4; d[3] = q3; d[2] = q2; d[1] = q1; d[0] = q0;
+            --deg;
+            x = mk(0.0, 0.0);
+            it = 0;
+        }
+    }
+    // last two roots: d2 z^2 + d1 z + d0 (stable quadratic formula)
+    {
+        const cd disc = cfma(scale(-4.0, d[2]), d[0], csq(d[1]));
+        cd sq = csqrt_(disc);
+        if (re_mulc(d[1], sq) < 0.0) sq = -sq;       // Re(conj(d1) sq) >= 0
+        const cd qq = scale(-0.5, d[1] + sq);
+        z[1] = cmul(qq, crcp(d[2]));
+        z[0] = cmul(d[0], crcp(qq));
+    }
+    // Newton polish on the full polynomial
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        if (k < deg0) {
+            cd zk = z[k];
+#pragma unroll 1
+            for (int j = 0; j < 4; ++j) {
+                cd p, dp;
+                horner2(c, zk, p, dp);
+                MLM_COUNT(newton_evals);
+                const cd dz = cmul(p, crcp(dp));
+                const double dz2 = norm2(dz);
+                if (!(dz2 < 1e300)) break;            // p'=0 or overflow: keep the deflated root
+                zk = zk - dz;
+                if (dz2 <= 1e-18 * norm2(zk)) break;  // quadratic: next step would be < 1e-18 |z|
+                if (j == 3) flags |= MLM_FLAG_NOCONV;
+            }
+            z[k] = zk;
+        }
+    }
+    return deg0;
+}
+
+// ---------------------------------------------------------------------------------------
+// (d)+(e) one image: W_2..W_6 from r1 = 1/z, r2 = 1/(z+s); mu0, mu2, mu4
+// ---------------------------------------------------------------------------------------
+struct ImageTerms {
+    double mu0, mu2, mu4;
+};
+
+// ORDER = 2: mu0, mu2 (quadrupole, needs W2..W4);  ORDER = 4: also mu4 (needs W2..W6)
+template <int ORDER>
+MLM_HD ImageTerms image_terms_from_W(cd W2, cd W3, cd W4, cd W5, cd W6) {
+    // F_j = conj(W_{j+1}) are the derivatives of conj(W1) with respect to zbar.
+    const cd w = W2;
+    const cd F2 = conj(W3), F3 = conj(W4);
+    const double w2n = norm2(w);
+    const double mu0 = rcp(1.0 - w2n);               // signed, multipoles.py:91
+    const cd ww = csq(w);
+    const cd www = cmul(ww, w);
+
+    // order 2:  R20 = F2 w^2, R11 = F2 w, R02 = F2;   u_mn = mu0 (conj(R_nm) + w R_mn)
+    const cd R20 = cmul(F2, ww), R11 = cmul(F2, w), R02 = F2;
+    const cd u20 = scale(mu0, cfma(w, R20, conj(R02)));
+    const cd u11 = scale(mu0, cfma(w, R11, conj(R11)));
+    const cd u02 = scale(mu0, cfma(w, R02, conj(R20)));
+
+    // order 3
+    const cd t1 = cmul(u20, w), t2 = cmul(u11, w), t3 = cmul(u02, w);
+    const cd R30 = cfma(F3, www, cmul(F2, scale(3.0, t1)));
+    const cd R21 = cfma(F3, ww, cmul(F2, rfma(2.0, t2, u20)));
+    const cd R12 = cfma(F3, w, cmul(F2, rfma(2.0, u11, t3)));
+    const cd R03 = F3 + cmul(F2, scale(3.0, u02));
+    const cd u30 = scale(mu0, cfma(w, R30, conj(R03)));
+    const cd u21 = scale(mu0, cfma(w, R21, conj(R12)));
+    const cd u12 = scale(mu0, cfma(w, R12, conj(R21)));
+    const cd u03 = scale(mu0, cfma(w, R03, conj(R30)));
+
+    ImageTerms out;
+    out.mu0 = mu0;
+    const double mu02 = mu0 * mu0;
+    const double mu04 = mu02 * mu02;
+    // lap1 = 2 Re(R21) + |u02|^2 - |u20|^2
+    const double lap1 = fma(2.0, R21.x, norm2(u02) - norm2(u20));
+    out.mu2 = mu04 * lap1;
+    out.mu4 = 0.0;
+    if (ORDER >= 4) {
+        const cd F4 = conj(W5), F5 = conj(W6);
+        // shared products
+        const cd p_u21w = cmul(u21, w);
+        const cd p_u12w = cmul(u12, w);
+        const cd p_u11u20 = cmul(u11, u20);
+        const cd p_u11u02 = cmul(u11, u02);
+        const cd p_u11sq = csq(u11);
+        const cd p_u02u20 = cmul(u02, u20);
+        const cd t2w = cmul(t2, w);                   // u11 w^2
+        const cd t3w = cmul(t3, w);                   // u02 w^2
+        // order 4 (only 31, 22, 13 are needed)
+        // R31 = F2 (3 u21 w + 3 u11 u20 + u30) + 3 F3 (u11 w^2 + u20 w) + F4 w^3
+        cd R31 = cmul(F2, rfma(3.0, p_u21w + p_u11u20, u30));
+        R31 = cfma(F3, scale(3.0, t2w + t1), R31);
+        R31 = cfma(F4, www, R31);
+        // R22 = F2 (2 u12 w + 2 u11^2 + u02 u20 + 2 u21) + F3 (u02 w^2 + 4 u11 w + u20) + F4 w^2
+        cd R22 = cmul(F2, rfma(2.0, p_u12w + p_u11sq + u21, p_u02u20));
+        R22 = cfma(F3, rfma(4.0, t2, t3w + u20), R22);
+        R22 = cfma(F4, ww, R22);
+        // R13 = F2 (3 u12 + 3 u11 u02 + w u03) + 3 F3 (u11 + w u02) + F4 w
+        cd R13 = cmul(F2, rfma(3.0, u12 + p_u11u02, cmul(w, u03)));
+        R13 = cfma(F3, scale(3.0, u11 + t3), R13);
+        R13 = cfma(F4, w, R13);
+        const cd u31 = scale(mu0, cfma(w, R31, conj(R13)));
+        const cd u22 = scale(mu0, cfma(w, R22, conj(R22)));
+        const cd u13 = scale(mu0, cfma(w, R13, conj(R31)));
+        // order 5: only Re(R32) survives in lap2
+        // S2 = 3 u22 w + 6 u11 u21 + 3 u12 u20 + u02 u30 + 2 u31
+        cd S2 = cfma(u02, u30, scale(2.0, u31));
+        S2 = rfma(3.0, cfma(u22, w, cmul(u12, u20)), S2);
+        S2 = rfma(6.0, cmul(u11, u21), S2);
+        // S3 = w (3 u12 w + 6 u11^2 + 3 u02 u20 + 6 u21) + 6 u11 u20 + u30
+        cd in3 = rfma(3.0, p_u12w + p_u02u20, scale(6.0, p_u11sq + u21));
+        cd S3 = cfma(w, in3, rfma(6.0, p_u11u20, u30));
+        // S4 = w^2 (u02 w + 6 u11) + 3 u20 w
+        cd S4 = cfma(ww, rfma(6.0, u11, t3), scale(3.0, t1));
+        // Re(R32) = Re(F2 S2 + F3 S3 + F4 S4 + F5 w^3)
+        const double reR32 = re_mul(F2, S2) + re_mul(F3, S3) + re_mul(F4, S4) + re_mul(F5, www);
+        // lap2 = 2 Re R32 + 4 Re(u02 conj u13) - 4 Re(u20 conj u31)
+        //        + |u03|^2 - |u30|^2 + 3 |u12|^2 - 3 |u21|^2
+        double lap2 = 2.0 * reR32;
+        lap2 = fma(4.0, re_mulc(u02, u13) - re_mulc(u20, u31), lap2);
+        lap2 += norm2(u03) - norm2(u30);
+        lap2 = fma(3.0, norm2(u12) - norm2(u21), lap2);
+        out.mu4 = 2.0 * (mu04 * mu02) * lap2;
+    }
+    return out;
+}
+
+// Source-size / limb-darkening factors (multipoles.py:145-146):
+//   A2 term: mu0 + h2 mu2,  A4 term: ... + h4 mu4
+struct SourceFactors {
+    double h2, h4;
+};
+MLM_HD SourceFactors source_factors(double rho, double Gamma) {
+    SourceFactors f;
+    const double r2 = rho * rho;
+    f.h2 = 0.5 * (1.0 - 0.2 * Gamma) * r2;
+    f.h4 = (1.0 / 24.0) * (1.0 - (11.0 / 35.0) * Gamma) * (r2 * r2);
+    return f;
+}
+
+struct PointResult {
+    double A0, A2, A4;
+    unsigned nimg;
+    unsigned flags;
+};
+
+// (c)+(d)+(e): given the polynomial roots, select the physical images, polish them on the
+// lens equation itself, and accumulate A0/A2/A4.
+template <int ORDER>
+MLM_HD void accumulate_images(const LensTable& T, const SourceFactors sf, cd zeta, const cd z[5],
+                              PointResult& out) {
+    double A0 = 0.0, A2 = 0.0, A4 = 0.0, minJ = 1e300;
+    unsigned n = 0, flags = out.flags;
+    // The image loop is kept rolled (5 x ~500 instructions would overflow the instruction
+    // cache); the roots rotate through zr[0] so that no register array is indexed dynamically.
+    cd zr[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) zr[k] = z[k];
+#pragma unroll 1
+    for (int k = 0; k < 5; ++k) {
+        cd zk = zr[0];
+        zr[0] = zr[1]; zr[1] = zr[2]; zr[2] = zr[3]; zr[3] = zr[4];
+        cd zs = mk(zk.x + T.s, zk.y);
+        cd r1 = crcp(zk), r2 = crcp(zs);
+        // residual of the lens equation, multipoles.py:182-183
+        cd W1 = rfma(T.alpha[1], r1, scale(T.beta[1], r2));
+        cd f = zk - zeta - conj(W1);
+        const double f2 = norm2(f);
+        if (f2 > 1e-14 && f2 < 1e-10) flags |= MLM_FLAG_AMBIG;
+        if (!(f2 < 1e-8)) continue;                   // NaN residual -> rejected, like NumPy
+        // One Newton step on the lens equation z - zeta - conj(W1(z)) = 0 (well conditioned,
+        // unlike the polynomial at small q):  dz = -(f + conj(W2) conj(f)) / (1 - |W2|^2)
+        bool phys = (f2 < 1e-12);                     // the reference's test, multipoles.py:183
+        {
+            const cd r1s = csq(r1), r2s = csq(r2);
+            const cd W2 = rfma(T.alpha[2], r1s, scale(T.beta[2], r2s));
+            const double iJ = rcp(1.0 - norm2(W2));
+            const cd dz = scale(-iJ, cjfma(W2, conj(f), f));
+            const double dz2 = norm2(dz);
+            // physical root: only ever a tiny correction.  Residual in (1e-6, 1e-4): the root
+            // noise of an ill-conditioned polynomial, amplified by |W2| >> 1 (faint image next
+            // to a low-mass lens), can push a true image over the threshold; it is kept iff a
+            // minute Newton step (< 1e-8) lands on an exact solution.
+            if (dz2 < (phys ? 1e-10 : 1e-16)) {
+                zk = zk + dz;
+                zs = mk(zk.x + T.s, zk.y);
+                r1 = crcp(zk);
+                r2 = crcp(zs);
+                if (!phys) {
+                    W1 = rfma(T.alpha[1], r1, scale(T.beta[1], r2));
+                    f = zk - zeta - conj(W1);
+                    phys = (norm2(f) < 1e-18);
+                }
+            }
+        }
+        if (!phys) continue;
+        ++n;
+        // W_k = alpha_k r1^k + beta_k r2^k, multipoles.py:197-201
+        const cd a2 = csq(r1), b2 = csq(r2);
+        const cd a3 = cmul(a2, r1), b3 = cmul(b2, r2);
+        const cd a4 = csq(a2), b4 = csq(b2);
+        const cd W2 = rfma(T.alpha[2], a2, scale(T.beta[2], b2));
+        const cd W3 = rfma(T.alpha[3], a3, scale(T.beta[3], b3));
+        const cd W4 = rfma(T.alpha[4], a4, scale(T.beta[4], b4));
+        cd W5 = mk(0.0, 0.0), W6 = mk(0.0, 0.0);
+        if (ORDER >= 4) {
+            const cd a5 = cmul(a4, r1), b5 = cmul(b4, r2);
+            const cd a6 = csq(a3), b6 = csq(b3);
+            W5 = rfma(T.alpha[5], a5, scale(T.beta[5], b5));
+            W6 = rfma(T.alpha[6], a6, scale(T.beta[6], b6));
+        }
+        const ImageTerms t = image_terms_from_W<ORDER>(W2, W3, W4, W5, W6);
+        const double v2 = fma(sf.h2, t.mu2, t.mu0);
+        A0 += fabs(t.mu0);
+        A2 += fabs(v2);
+        if (ORDER >= 4) A4 += fabs(fma(sf.h4, t.mu4, v2));
+        minJ = fmin(minJ, fabs(1.0 - norm2(W2)));
+    }
+    if (minJ < 1e-3) flags |= MLM_FLAG_NEARCRIT;
+    if (ORDER >= 4 && fabs(A4 - A2) > fabs(A2 - A0)) flags |= MLM_FLAG_SERIES;
+    out.A0 = A0; out.A2 = A2; out.A4 = A4; out.nimg = n; out.flags = flags;
+}
+
+// whole path for one source position (cold start)
+template <int ORDER>
+MLM_HD PointResult point_magnification(const LensTable& T, const SourceFactors sf, cd zeta) {
+    cd c[6], z[5];
+    PointResult out;
+    out.flags = 0;
+    lens_polynomial(T, zeta, c);
+    solve_roots(c, z, out.flags);
+    accumulate_images<ORDER>(T, sf, zeta, z, out);
+    return out;
+}
+
+// ---------------------------------------------------------------------------------------
+// Literal (xi, eta) evaluation for user-supplied W_k tables: drop-in for
+// quadrupole(Wk,...) / hexadecapole(Wk,...), multipoles.py:12-65 / 67-148.  Unlike
+// image_terms_from_W nothing is assumed about where the W_k come from, and the result
+// keeps the reference's definitions of every intermediate a_{kl}.
+// The Q_{kl} sums are generated from set-partition counts (see tools/gen_qkl.py).
+// ---------------------------------------------------------------------------------------
+MLM_HD cd akl(double mu, cd W2, cd Q) {              // multipoles.py:150-154
+    return scale(mu, cjfma(W2, Q, conj(Q)));
+}
+
+}  // namespace mlm

@@ -1,0 +1,706 @@
+// mlm_kernels.cu -- CUDA kernels (sm_100a, FP64) and the C ABI of libmlmultipoles.so.
+//
+// One thread = one source position; everything between the 16-byte coalesced load of zeta
+// (or the in-kernel generation of the map / light-curve coordinate) and the coalesced SoA
+// stores of A0/A2/A4/nimg/flags lives in registers (mlm_core.cuh).  The workload is bound by
+// the FP64 pipe (~4 k DFMA-class instructions per position vs 16-41 bytes of HBM traffic),
+// so there is no shared-memory tiling and no tensor-core path; the per-(s,q) table sits in
+// the constant bank (kernel parameter) for maps / point lists and in shared memory for the
+// batched model grid.
+//
+// Reference interfaces replaced: see include/mlmultipoles.h.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "../../include/mlmultipoles.h"
+#include "mlm_core.cuh"
+#include "mlm_qkl_generated.cuh"
+
+using namespace mlm;
+
+#define MLM_BLOCK 128
+
+// ------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_result(const PointResult& r, int64_t i, double* __restrict__ A0,
+                                             double* __restrict__ A2, double* __restrict__ A4,
+                                             uint8_t* __restrict__ nimg, uint8_t* __restrict__ flags) {
+    A0[i] = r.A0;
+    A2[i] = r.A2;
+    A4[i] = r.A4;
+    if (nimg) nimg[i] = (uint8_t)r.nimg;
+    if (flags) flags[i] = (uint8_t)r.flags;
+}
+
+// K1a: arbitrary list of positions, one lens.
+template <int ORDER>
+__global__ void __launch_bounds__(MLM_BLOCK)
+k_points(const __grid_constant__ LensTable T, const SourceFactors sf, const double2* __restrict__ zeta, int64_t n,
+         double* __restrict__ A0, double* __restrict__ A2, double* __restrict__ A4, uint8_t* __restrict__ nimg,
+         uint8_t* __restrict__ flags) {
+    const int64_t i = (int64_t)blockIdx.x * MLM_BLOCK + threadIdx.x;
+    if (i >= n) return;
+    const double2 zz = __ldg(zeta + i);               // one 16-byte load per thread, coalesced
+    const PointResult r = point_magnification<ORDER>(T, sf, mk(zz.x, zz.y));
+    store_result(r, i, A0, A2, A4, nimg, flags);
+}
+
+// K1b: magnification map, zeta generated in-kernel (no input traffic).
+// blockIdx.x tiles the columns, blockIdx.y strides over the rows of this shard.
+template <int ORDER>
+__global__ void __launch_bounds__(MLM_BLOCK)
+k_map(const __grid_constant__ LensTable T, const SourceFactors sf, double x0, double y0, double dx, double dy,
+      double shift, int64_t nx, int64_t row0, int64_t nrows, double* __restrict__ A0, double* __restrict__ A2,
+      double* __restrict__ A4, uint8_t* __restrict__ nimg, uint8_t* __restrict__ flags) {
+    const int64_t col = (int64_t)blockIdx.x * MLM_BLOCK + threadIdx.x;
+    if (col >= nx) return;
+    // x = x0 + (col + 0.5) dx with two roundings (no FMA), so that host code can reproduce
+    // the coordinates bit for bit with the same expression.
+    const double x = __dadd_rn(__dadd_rn(x0, __dmul_rn((double)col + 0.5, dx)), -shift);
+    for (int64_t r = blockIdx.y; r < nrows; r += gridDim.y) {
+        const double y = __dadd_rn(y0, __dmul_rn((double)(row0 + r) + 0.5, dy));
+        const PointResult res = point_magnification<ORDER>(T, sf, mk(x, y));
+        store_result(res, r * nx + col, A0, A2, A4, nimg, flags);
+    }
+}
+
+// K1c: batched model grid; blockIdx.y = model, the block stages that model's table in shared
+// memory, threads run over epochs.
+template <int ORDER>
+__global__ void __launch_bounds__(MLM_BLOCK)
+k_models(const double* __restrict__ s, const double* __restrict__ q, const double* __restrict__ rho,
+         const double* __restrict__ Gamma, const double* __restrict__ u0, const double* __restrict__ alpha,
+         int64_t M, double tau0, double dtau, int64_t Tn, double* __restrict__ A0, double* __restrict__ A2,
+         double* __restrict__ A4, uint8_t* __restrict__ nimg, uint8_t* __restrict__ flags) {
+    __shared__ LensTable T;
+    __shared__ SourceFactors sf;
+    __shared__ double rot[3];                          // cos(alpha), sin(alpha), shift
+    for (int64_t m = blockIdx.y; m < M; m += gridDim.y) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const double sm = s[m], qm = q[m];
+            make_table(sm, qm, &T);
+            sf = source_factors(rho[m], Gamma[m]);
+            double sa, ca;
+            sincos(alpha[m], &sa, &ca);
+            rot[0] = ca; rot[1] = sa; rot[2] = sm * qm / (1.0 + qm);
+        }
+        __syncthreads();
+        const double u = u0[m];
+        for (int64_t t = (int64_t)blockIdx.x * MLM_BLOCK + threadIdx.x; t < Tn; t += (int64_t)gridDim.x * MLM_BLOCK) {
+            const double tau = __dadd_rn(tau0, __dmul_rn((double)t, dtau));
+            // zeta_cm = (tau + i u0) (cos a + i sin a), then shift to the primary frame
+            const double zx = __dadd_rn(__dadd_rn(__dmul_rn(tau, rot[0]), -__dmul_rn(u, rot[1])), -rot[2]);
+            const double zy = __dadd_rn(__dmul_rn(tau, rot[1]), __dmul_rn(u, rot[0]));
+            const PointResult r = point_magnification<ORDER>(T, sf, mk(zx, zy));
+            store_result(r, m * Tn + t, A0, A2, A4, nimg, flags);
+        }
+    }
+}
+
+// K3: roots only (drop-in for _solvelenseq)
+__global__ void __launch_bounds__(MLM_BLOCK)
+k_solve(const __grid_constant__ LensTable T, const double2* __restrict__ zeta, int64_t n, double2* __restrict__ roots) {
+    const int64_t i = (int64_t)blockIdx.x * MLM_BLOCK + threadIdx.x;
+    if (i >= n) return;
+    const double2 zz = __ldg(zeta + i);
+    cd c[6], z[5];
+    unsigned fl = 0;
+    lens_polynomial(T, mk(zz.x, zz.y), c);
+    solve_roots(c, z, fl);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) roots[5 * i + k] = make_double2(z[k].x, z[k].y);
+}
+
+// K2: literal quadrupole / hexadecapole on a user-supplied (7, n) Wk table.
+// Per-block partial sums (fixed tree order -> deterministic), reduced by k_from_wk_final.
+template <int ORDER>
+__global__ void __launch_bounds__(MLM_BLOCK)
+k_from_wk(const double2* __restrict__ Wk, int64_t n, double h2, double h4, double* __restrict__ partial) {
+    double a0 = 0.0, a2 = 0.0, a4 = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * MLM_BLOCK + threadIdx.x; i < n; i += (int64_t)gridDim.x * MLM_BLOCK) {
+        const double2 w2 = __ldg(Wk + 2 * n + i), w3 = __ldg(Wk + 3 * n + i), w4 = __ldg(Wk + 4 * n + i);
+        double2 w5 = make_double2(0.0, 0.0), w6 = w5;
+        if (ORDER >= 4) { w5 = __ldg(Wk + 5 * n + i); w6 = __ldg(Wk + 6 * n + i); }
+        const ImageTerms t = image_terms_literal<ORDER>(mk(w2.x, w2.y), mk(w3.x, w3.y), mk(w4.x, w4.y),
+                                                        mk(w5.x, w5.y), mk(w6.x, w6.y));
+        const double v2 = fma(h2, t.mu2, t.mu0);
+        a0 += fabs(t.mu0);
+        a2 += fabs(v2);
+        if (ORDER >= 4) a4 += fabs(fma(h4, t.mu4, v2));
+    }
+    __shared__ double sh[3][MLM_BLOCK / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a0 += __shfl_down_sync(0xffffffffu, a0, o);
+        a2 += __shfl_down_sync(0xffffffffu, a2, o);
+        a4 += __shfl_down_sync(0xffffffffu, a4, o);
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { sh[0][w] = a0; sh[1][w] = a2; sh[2][w] = a4; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t0 = 0.0, t2 = 0.0, t4 = 0.0;
+        for (int k = 0; k < MLM_BLOCK / 32; ++k) { t0 += sh[0][k]; t2 += sh[1][k]; t4 += sh[2][k]; }
+        partial[3 * blockIdx.x + 0] = t0;
+        partial[3 * blockIdx.x + 1] = t2;
+        partial[3 * blockIdx.x + 2] = t4;
+    }
+}
+
+__global__ void k_from_wk_final(const double* __restrict__ partial, int nblocks, int nout, double* __restrict__ out) {
+    if (threadIdx.x < nout) {
+        double t = 0.0;
+        for (int b = 0; b < nblocks; ++b) t += partial[3 * b + threadIdx.x];
+        out[threadIdx.x] = t;
+    }
+}
+
+// _akl, elementwise
+__global__ void __launch_bounds__(MLM_BLOCK)
+k_akl(const double2* __restrict__ mu, const double2* __restrict__ W2, const double2* __restrict__ Q, int64_t n,
+      double2* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * MLM_BLOCK + threadIdx.x;
+    if (i >= n) return;
+    const double2 m = __ldg(mu + i), w = __ldg(W2 + i), qq = __ldg(Q + i);
+    const cd a = cmul(mk(m.x, m.y), akl(1.0, mk(w.x, w.y), mk(qq.x, qq.y)));
+    out[i] = make_double2(a.x, a.y);
+}
+
+// FP64 FMA throughput microbenchmark: 8 independent DFMA chains per thread.
+__global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    const double sum = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (sum == 12345.678) out[0] = sum;               // never true; keeps the chains alive
+}
+
+// ------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------
+struct mlm_context {
+    int device = 0;
+    cudaStream_t stream[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    void* dbuf = nullptr;                              // device scratch for *_host entry points
+    size_t dbuf_bytes = 0;
+    double* partial = nullptr;                         // from_wk partial sums
+    int partial_blocks = 0;
+    std::atomic<int64_t> launches{0};
+    std::string err;
+    int sm_count = 148;
+};
+
+static std::string g_err;
+static std::mutex g_mu;
+
+static int fail(mlm_context* ctx, int code, const char* what) {
+    std::string msg = std::string(what);
+    if (code > 0) msg += std::string(": ") + cudaGetErrorString((cudaError_t)code);
+    if (ctx) ctx->err = msg;
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_err = msg;
+    return code;
+}
+
+#define CK(call)                                                       \
+    do {                                                               \
+        cudaError_t e_ = (call);                                       \
+        if (e_ != cudaSuccess) return fail(ctx, (int)e_, #call);       \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+static int ensure_dbuf(mlm_context* ctx, size_t bytes) {
+    if (bytes <= ctx->dbuf_bytes) return 0;
+    if (ctx->dbuf) CK(cudaFree(ctx->dbuf));
+    ctx->dbuf = nullptr;
+    ctx->dbuf_bytes = 0;
+    CK(cudaMalloc(&ctx->dbuf, bytes));
+    ctx->dbuf_bytes = bytes;
+    return 0;
+}
+
+static inline cudaStream_t pick(mlm_context* ctx, void* stream) {
+    return stream ? (cudaStream_t)stream : ctx->stream[0];
+}
+
+static bool bad_lens(double s, double q) { return !(s > 0.0) || !(q > 0.0) || !std::isfinite(s) || !std::isfinite(q); }
+
+extern "C" {
+
+const char* mlm_version(void) { return "microlensing_b200 0.1.0 (sm_100a)"; }
+
+const char* mlm_last_error(mlm_context* ctx) {
+    if (ctx) return ctx->err.c_str();
+    std::lock_guard<std::mutex> lk(g_mu);
+    return g_err.c_str();
+}
+
+int mlm_create(int device, mlm_context** out) {
+    mlm_context* ctx = nullptr;
+    if (!out) return fail(nullptr, MLM_EINVAL, "mlm_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess) return fail(nullptr, (int)e, "mlm_create: no CUDA device (there is no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(nullptr, MLM_EINVAL, "mlm_create: bad device index");
+    ctx = new (std::nothrow) mlm_context();
+    if (!ctx) return fail(nullptr, MLM_ENOMEM, "mlm_create: out of host memory");
+    ctx->device = device;
+    DeviceGuard g(device);
+    for (int i = 0; i < 2; ++i) {
+        e = cudaStreamCreateWithFlags(&ctx->stream[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming);
+        if (e != cudaSuccess) {
+            int rc = fail(nullptr, (int)e, "mlm_create: stream/event creation");
+            delete ctx;
+            return rc;
+        }
+    }
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    *out = ctx;
+    return 0;
+}
+
+int mlm_destroy(mlm_context* ctx) {
+    if (!ctx) return 0;
+    DeviceGuard g(ctx->device);
+    cudaDeviceSynchronize();
+    if (ctx->dbuf) cudaFree(ctx->dbuf);
+    if (ctx->partial) cudaFree(ctx->partial);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+        if (ctx->stream[i]) cudaStreamDestroy(ctx->stream[i]);
+    }
+    delete ctx;
+    return 0;
+}
+
+int mlm_launch_count(mlm_context* ctx, int64_t* out) {
+    if (!ctx || !out) return fail(ctx, MLM_EINVAL, "mlm_launch_count: NULL argument");
+    *out = ctx->launches.load();
+    return 0;
+}
+
+int mlm_synchronize(mlm_context* ctx) {
+    if (!ctx) return fail(ctx, MLM_EINVAL, "mlm_synchronize: NULL context");
+    DeviceGuard g(ctx->device);
+    CK(cudaStreamSynchronize(ctx->stream[0]));
+    CK(cudaStreamSynchronize(ctx->stream[1]));
+    return 0;
+}
+
+int mlm_alloc_host(mlm_context* ctx, int64_t bytes, void** out) {
+    if (!ctx || !out || bytes < 0) return fail(ctx, MLM_EINVAL, "mlm_alloc_host: bad argument");
+    DeviceGuard g(ctx->device);
+    *out = nullptr;
+    if (bytes == 0) return 0;
+    CK(cudaHostAlloc(out, (size_t)bytes, cudaHostAllocPortable));
+    return 0;
+}
+
+int mlm_free_host(mlm_context* ctx, void* p) {
+    if (!ctx) return fail(ctx, MLM_EINVAL, "mlm_free_host: NULL context");
+    if (!p) return 0;
+    DeviceGuard g(ctx->device);
+    CK(cudaFreeHost(p));
+    return 0;
+}
+
+// ---- fused path, device pointers --------------------------------------------------------------
+int mlm_points(mlm_context* ctx, double s, double q, double rho, double Gamma, const double* zeta, int64_t n,
+               int order, double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags, void* stream) {
+    if (!ctx) return fail(ctx, MLM_EINVAL, "mlm_points: NULL context");
+    if (n < 0 || (order != 2 && order != 4) || bad_lens(s, q)) return fail(ctx, MLM_EINVAL, "mlm_points: bad argument");
+    if (n == 0) return 0;
+    if (!zeta || !A0 || !A2 || !A4) return fail(ctx, MLM_EINVAL, "mlm_points: NULL buffer");
+    DeviceGuard g(ctx->device);
+    LensTable T;
+    make_table(s, q, &T);
+    const SourceFactors sf = source_factors(rho, Gamma);
+    const unsigned blocks = (unsigned)((n + MLM_BLOCK - 1) / MLM_BLOCK);
+    cudaStream_t st = pick(ctx, stream);
+    if (order == 4)
+        k_points<4><<<blocks, MLM_BLOCK, 0, st>>>(T, sf, (const double2*)zeta, n, A0, A2, A4, nimg, flags);
+    else
+        k_points<2><<<blocks, MLM_BLOCK, 0, st>>>(T, sf, (const double2*)zeta, n, A0, A2, A4, nimg, flags);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int mlm_map(mlm_context* ctx, double s, double q, double rho, double Gamma, double x0, double y0, double dx,
+            double dy, int64_t nx, int64_t row0, int64_t nrows, int order, double* A0, double* A2, double* A4,
+            uint8_t* nimg, uint8_t* flags, void* stream) {
+    if (!ctx) return fail(ctx, MLM_EINVAL, "mlm_map: NULL context");
+    if (nx < 0 || nrows < 0 || (order != 2 && order != 4) || bad_lens(s, q))
+        return fail(ctx, MLM_EINVAL, "mlm_map: bad argument");
+    if (nx == 0 || nrows == 0) return 0;
+    if (!A0 || !A2 || !A4) return fail(ctx, MLM_EINVAL, "mlm_map: NULL buffer");
+    DeviceGuard g(ctx->device);
+    LensTable T;
+    make_table(s, q, &T);
+    const SourceFactors sf = source_factors(rho, Gamma);
+    const double shift = s * q / (1.0 + q);            // multipoles.py:178
+    dim3 grid((unsigned)((nx + MLM_BLOCK - 1) / MLM_BLOCK), (unsigned)(nrows < 65535 ? nrows : 65535));
+    cudaStream_t st = pick(ctx, stream);
+    if (order == 4)
+        k_map<4><<<grid, MLM_BLOCK, 0, st>>>(T, sf, x0, y0, dx, dy, shift, nx, row0, nrows, A0, A2, A4, nimg, flags);
+    else
+        k_map<2><<<grid, MLM_BLOCK, 0, st>>>(T, sf, x0, y0, dx, dy, shift, nx, row0, nrows, A0, A2, A4, nimg, flags);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int mlm_models(mlm_context* ctx, const double* s, const double* q, const double* rho, const double* Gamma,
+               const double* u0, const double* alpha, int64_t M, double tau0, double dtau, int64_t Tn, int order,
+               double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags, void* stream) {
+    if (!ctx) return fail(ctx, MLM_EINVAL, "mlm_models: NULL context");
+    if (M < 0 || Tn < 0 || (order != 2 && order != 4)) return fail(ctx, MLM_EINVAL, "mlm_models: bad argument");
+    if (M == 0 || Tn == 0) return 0;
+    if (!s || !q || !rho || !Gamma || !u0 || !alpha || !A0 || !A2 || !A4)
+        return fail(ctx, MLM_EINVAL, "mlm_models: NULL buffer");
+    DeviceGuard g(ctx->device);
+    int64_t bx = (Tn + MLM_BLOCK - 1) / MLM_BLOCK;
+    if (bx > 1024) bx = 1024;
+    dim3 grid((unsigned)bx, (unsigned)(M < 65535 ? M : 65535));
+    cudaStream_t st = pick(ctx, stream);
+    if (order == 4)
+        k_models<4><<<grid, MLM_BLOCK, 0, st>>>(s, q, rho, Gamma, u0, alpha, M, tau0, dtau, Tn, A0, A2, A4, nimg, flags);
+    else
+        k_models<2><<<grid, MLM_BLOCK, 0, st>>>(s, q, rho, Gamma, u0, alpha, M, tau0, dtau, Tn, A0, A2, A4, nimg, flags);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int mlm_from_wk(mlm_context* ctx, const double* Wk, int64_t n, int order, double rho, double Gamma, double* out,
+                void* stream) {
+    if (!ctx) return fail(ctx, MLM_EINVAL, "mlm_from_wk: NULL context");
+    if (n < 0 || (order != 2 && order != 4) || !out) return fail(ctx, MLM_EINVAL, "mlm_from_wk: bad argument");
+    if (n > 0 && !Wk) return fail(ctx, MLM_EINVAL, "mlm_from_wk: NULL Wk");
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = pick(ctx, stream);
+    const int nout = order == 4 ? 3 : 2;
+    if (n == 0) {                                      // zero images -> zeros
+        CK(cudaMemsetAsync(out, 0, nout * sizeof(double), st));
+        return 0;
+    }
+    int64_t blocks = (n + MLM_BLOCK - 1) / MLM_BLOCK;
+    if (blocks > 1184) blocks = 1184;                  // 8 x 148
+    if (ctx->partial_blocks < blocks) {
+        if (ctx->partial) CK(cudaFree(ctx->partial));
+        ctx->partial = nullptr;
+        ctx->partial_blocks = 0;
+        CK(cudaMalloc(&ctx->partial, 1184 * 3 * sizeof(double)));
+        ctx->partial_blocks = 1184;
+    }
+    const SourceFactors sf = source_factors(rho, Gamma);
+    if (order == 4)
+        k_from_wk<4><<<(unsigned)blocks, MLM_BLOCK, 0, st>>>((const double2*)Wk, n, sf.h2, sf.h4, ctx->partial);
+    else
+        k_from_wk<2><<<(unsigned)blocks, MLM_BLOCK, 0, st>>>((const double2*)Wk, n, sf.h2, sf.h4, ctx->partial);
+    k_from_wk_final<<<1, 32, 0, st>>>(ctx->partial, (int)blocks, nout, out);
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int mlm_solve(mlm_context* ctx, double s, double q, const double* zeta, int64_t n, double* roots, void* stream) {
+    if (!ctx) return fail(ctx, MLM_EINVAL, "mlm_solve: NULL context");
+    if (n < 0 || bad_lens(s, q)) return fail(ctx, MLM_EINVAL, "mlm_solve: bad argument");
+    if (n == 0) return 0;
+    if (!zeta || !roots) return fail(ctx, MLM_EINVAL, "mlm_solve: NULL buffer");
+    DeviceGuard g(ctx->device);
+    LensTable T;
+    make_table(s, q, &T);
+    const unsigned blocks = (unsigned)((n + MLM_BLOCK - 1) / MLM_BLOCK);
+    k_solve<<<blocks, MLM_BLOCK, 0, pick(ctx, stream)>>>(T, (const double2*)zeta, n, (double2*)roots);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int mlm_akl(mlm_context* ctx, const double* mu, const double* W2, const double* Q, int64_t n, double* out,
+            void* stream) {
+    if (!ctx) return fail(ctx, MLM_EINVAL, "mlm_akl: NULL context");
+    if (n < 0) return fail(ctx, MLM_EINVAL, "mlm_akl: bad argument");
+    if (n == 0) return 0;
+    if (!mu || !W2 || !Q || !out) return fail(ctx, MLM_EINVAL, "mlm_akl: NULL buffer");
+    DeviceGuard g(ctx->device);
+    const unsigned blocks = (unsigned)((n + MLM_BLOCK - 1) / MLM_BLOCK);
+    k_akl<<<blocks, MLM_BLOCK, 0, pick(ctx, stream)>>>((const double2*)mu, (const double2*)W2, (const double2*)Q, n, (double2*)out);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// ---- host-buffer entry points -------------------------------------------------------------------
+// Layout of the device scratch for n positions: [zeta 16n | A0 8n | A2 8n | A4 8n | nimg n | flags n]
+struct Scratch {
+    double *zeta, *A0, *A2, *A4;
+    uint8_t *nimg, *flags;
+};
+static int carve(mlm_context* ctx, int64_t n, bool with_zeta, Scratch* sc) {
+    const size_t npad = ((size_t)n + 255) & ~(size_t)255;
+    const size_t bytes = npad * ((with_zeta ? 16 : 0) + 24 + 2);
+    int rc = ensure_dbuf(ctx, bytes);
+    if (rc) return rc;
+    char* p = (char*)ctx->dbuf;
+    sc->zeta = (double*)p;
+    if (with_zeta) p += npad * 16;
+    sc->A0 = (double*)p; p += npad * 8;
+    sc->A2 = (double*)p; p += npad * 8;
+    sc->A4 = (double*)p; p += npad * 8;
+    sc->nimg = (uint8_t*)p; p += npad;
+    sc->flags = (uint8_t*)p;
+    return 0;
+}
+
+// copy one chunk of results back on `st`
+static int d2h_chunk(mlm_context* ctx, const Scratch& sc, int64_t off, int64_t cnt, double* A0, double* A2,
+                     double* A4, uint8_t* nimg, uint8_t* flags, cudaStream_t st) {
+    CK(cudaMemcpyAsync(A0 + off, sc.A0 + off, cnt * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(A2 + off, sc.A2 + off, cnt * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(A4 + off, sc.A4 + off, cnt * 8, cudaMemcpyDeviceToHost, st));
+    if (nimg) CK(cudaMemcpyAsync(nimg + off, sc.nimg + off, cnt, cudaMemcpyDeviceToHost, st));
+    if (flags) CK(cudaMemcpyAsync(flags + off, sc.flags + off, cnt, cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+
+#define MLM_CHUNK_POINTS (int64_t(1) << 21)
+
+int mlm_points_host(mlm_context* ctx, double s, double q, double rho, double Gamma, const double* zeta, int64_t n,
+                    int order, double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags) {
+    if (!ctx) return fail(ctx, MLM_EINVAL, "mlm_points_host: NULL context");
+    if (n < 0 || (order != 2 && order != 4) || bad_lens(s, q))
+        return fail(ctx, MLM_EINVAL, "mlm_points_host: bad argument");
+    if (n == 0) return 0;
+    if (!zeta || !A0 || !A2 || !A4) return fail(ctx, MLM_EINVAL, "mlm_points_host: NULL buffer");
+    DeviceGuard g(ctx->device);
+    Scratch sc;
+    int rc = carve(ctx, n, true, &sc);
+    if (rc) return rc;
+    // chunks alternate between the two streams: H2D(k+1) and D2H(k-1) overlap kernel(k)
+    int k = 0;
+    for (int64_t off = 0; off < n; off += MLM_CHUNK_POINTS, ++k) {
+        const int64_t cnt = (n - off < MLM_CHUNK_POINTS) ? (n - off) : MLM_CHUNK_POINTS;
+        cudaStream_t st = ctx->stream[k & 1];
+        CK(cudaMemcpyAsync(sc.zeta + 2 * off, zeta + 2 * off, cnt * 16, cudaMemcpyHostToDevice, st));
+        rc = mlm_points(ctx, s, q, rho, Gamma, sc.zeta + 2 * off, cnt, order, sc.A0 + off, sc.A2 + off, sc.A4 + off,
+                        sc.nimg + off, sc.flags + off, st);
+        if (rc) return rc;
+        rc = d2h_chunk(ctx, sc, off, cnt, A0, A2, A4, nimg, flags, st);
+        if (rc) return rc;
+    }
+    CK(cudaStreamSynchronize(ctx->stream[0]));
+    CK(cudaStreamSynchronize(ctx->stream[1]));
+    return 0;
+}
+
+int mlm_map_host(mlm_context* ctx, double s, double q, double rho, double Gamma, double x0, double y0, double dx,
+                 double dy, int64_t nx, int64_t row0, int64_t nrows, int order, double* A0, double* A2, double* A4,
+                 uint8_t* nimg, uint8_t* flags) {
+    if (!ctx) return fail(ctx, MLM_EINVAL, "mlm_map_host: NULL context");
+    if (nx < 0 || nrows < 0 || (order != 2 && order != 4) || bad_lens(s, q))
+        return fail(ctx, MLM_EINVAL, "mlm_map_host: bad argument");
+    if (nx == 0 || nrows == 0) return 0;
+    if (!A0 || !A2 || !A4) return fail(ctx, MLM_EINVAL, "mlm_map_host: NULL buffer");
+    DeviceGuard g(ctx->device);
+    const int64_t n = nx * nrows;
+    Scratch sc;
+    int rc = carve(ctx, n, false, &sc);
+    if (rc) return rc;
+    int64_t rows_per = MLM_CHUNK_POINTS / nx;
+    if (rows_per < 1) rows_per = 1;
+    int k = 0;
+    for (int64_t r = 0; r < nrows; r += rows_per, ++k) {
+        const int64_t nr = (nrows - r < rows_per) ? (nrows - r) : rows_per;
+        const int64_t off = r * nx, cnt = nr * nx;
+        cudaStream_t st = ctx->stream[k & 1];
+        rc = mlm_map(ctx, s, q, rho, Gamma, x0, y0, dx, dy, nx, row0 + r, nr, order, sc.A0 + off, sc.A2 + off,
+                     sc.A4 + off, sc.nimg + off, sc.flags + off, st);
+        if (rc) return rc;
+        rc = d2h_chunk(ctx, sc, off, cnt, A0, A2, A4, nimg, flags, st);
+        if (rc) return rc;
+    }
+    CK(cudaStreamSynchronize(ctx->stream[0]));
+    CK(cudaStreamSynchronize(ctx->stream[1]));
+    return 0;
+}
+
+int mlm_models_host(mlm_context* ctx, const double* s, const double* q, const double* rho, const double* Gamma,
+                    const double* u0, const double* alpha, int64_t M, double tau0, double dtau, int64_t Tn, int order,
+                    double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags) {
+    if (!ctx) return fail(ctx, MLM_EINVAL, "mlm_models_host: NULL context");
+    if (M < 0 || Tn < 0 || (order != 2 && order != 4)) return fail(ctx, MLM_EINVAL, "mlm_models_host: bad argument");
+    if (M == 0 || Tn == 0) return 0;
+    if (!s || !q || !rho || !Gamma || !u0 || !alpha || !A0 || !A2 || !A4)
+        return fail(ctx, MLM_EINVAL, "mlm_models_host: NULL buffer");
+    DeviceGuard g(ctx->device);
+    const int64_t n = M * Tn;
+    const size_t npad = ((size_t)n + 255) & ~(size_t)255;
+    const size_t mpad = ((size_t)M + 31) & ~(size_t)31;
+    int rc = ensure_dbuf(ctx, npad * 26 + mpad * 48);
+    if (rc) return rc;
+    Scratch sc;
+    rc = carve(ctx, n, false, &sc);
+    if (rc) return rc;
+    double* par = (double*)((char*)ctx->dbuf + npad * 26);
+    const double* hp[6] = {s, q, rho, Gamma, u0, alpha};
+    cudaStream_t st0 = ctx->stream[0];
+    for (int i = 0; i < 6; ++i) CK(cudaMemcpyAsync(par + i * mpad, hp[i], M * 8, cudaMemcpyHostToDevice, st0));
+    CK(cudaEventRecord(ctx->ev[0], st0));
+    CK(cudaStreamWaitEvent(ctx->stream[1], ctx->ev[0], 0));
+    int64_t models_per = MLM_CHUNK_POINTS / Tn;
+    if (models_per < 1) models_per = 1;
+    int k = 0;
+    for (int64_t m0 = 0; m0 < M; m0 += models_per, ++k) {
+        const int64_t nm = (M - m0 < models_per) ? (M - m0) : models_per;
+        const int64_t off = m0 * Tn, cnt = nm * Tn;
+        cudaStream_t st = ctx->stream[k & 1];
+        rc = mlm_models(ctx, par + m0, par + mpad + m0, par + 2 * mpad + m0, par + 3 * mpad + m0, par + 4 * mpad + m0,
+                        par + 5 * mpad + m0, nm, tau0, dtau, Tn, order, sc.A0 + off, sc.A2 + off, sc.A4 + off,
+                        sc.nimg + off, sc.flags + off, st);
+        if (rc) return rc;
+        rc = d2h_chunk(ctx, sc, off, cnt, A0, A2, A4, nimg, flags, st);
+        if (rc) return rc;
+    }
+    CK(cudaStreamSynchronize(ctx->stream[0]));
+    CK(cudaStreamSynchronize(ctx->stream[1]));
+    return 0;
+}
+
+int mlm_from_wk_host(mlm_context* ctx, const double* Wk, int64_t n, int order, double rho, double Gamma, double* out) {
+    if (!ctx) return fail(ctx, MLM_EINVAL, "mlm_from_wk_host: NULL context");
+    if (n < 0 || (order != 2 && order != 4) || !out) return fail(ctx, MLM_EINVAL, "mlm_from_wk_host: bad argument");
+    if (n > 0 && !Wk) return fail(ctx, MLM_EINVAL, "mlm_from_wk_host: NULL Wk");
+    DeviceGuard g(ctx->device);
+    const int nrows = order == 4 ? 7 : 5;              // rows 0..4 or 0..6 (rows 0-1 are skipped below)
+    const size_t wbytes = (size_t)(nrows - 2) * n * 16;
+    int rc = ensure_dbuf(ctx, (size_t)nrows * n * 16 + 64);
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream[0];
+    double* dW = (double*)ctx->dbuf;
+    double* dout = (double*)((char*)ctx->dbuf + (size_t)nrows * n * 16);
+    // rows 0-1 are uninitialised in the reference (np.empty, multipoles.py:186): never copied or read
+    if (n > 0) CK(cudaMemcpyAsync(dW + 4 * n, Wk + 4 * n, wbytes, cudaMemcpyHostToDevice, st));
+    rc = mlm_from_wk(ctx, dW, n, order, rho, Gamma, dout, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out, dout, (order == 4 ? 3 : 2) * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int mlm_solve_host(mlm_context* ctx, double s, double q, const double* zeta, int64_t n, double* roots) {
+    if (!ctx) return fail(ctx, MLM_EINVAL, "mlm_solve_host: NULL context");
+    if (n < 0 || bad_lens(s, q)) return fail(ctx, MLM_EINVAL, "mlm_solve_host: bad argument");
+    if (n == 0) return 0;
+    if (!zeta || !roots) return fail(ctx, MLM_EINVAL, "mlm_solve_host: NULL buffer");
+    DeviceGuard g(ctx->device);
+    int rc = ensure_dbuf(ctx, (size_t)n * 96);
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream[0];
+    double* dz = (double*)ctx->dbuf;
+    double* dr = dz + 2 * n;
+    CK(cudaMemcpyAsync(dz, zeta, n * 16, cudaMemcpyHostToDevice, st));
+    rc = mlm_solve(ctx, s, q, dz, n, dr, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(roots, dr, n * 80, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int mlm_akl_host(mlm_context* ctx, const double* mu, const double* W2, const double* Q, int64_t n, double* out) {
+    if (!ctx) return fail(ctx, MLM_EINVAL, "mlm_akl_host: NULL context");
+    if (n < 0) return fail(ctx, MLM_EINVAL, "mlm_akl_host: bad argument");
+    if (n == 0) return 0;
+    if (!mu || !W2 || !Q || !out) return fail(ctx, MLM_EINVAL, "mlm_akl_host: NULL buffer");
+    DeviceGuard g(ctx->device);
+    int rc = ensure_dbuf(ctx, (size_t)n * 64);
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream[0];
+    double* dmu = (double*)ctx->dbuf;
+    double* dW = dmu + 2 * n;
+    double* dQ = dW + 2 * n;
+    double* dO = dQ + 2 * n;
+    CK(cudaMemcpyAsync(dmu, mu, n * 16, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dW, W2, n * 16, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dQ, Q, n * 16, cudaMemcpyHostToDevice, st));
+    rc = mlm_akl(ctx, dmu, dW, dQ, n, dO, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out, dO, n * 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ---- measurement helpers ----------------------------------------------------------------------
+int mlm_fp64_peak(mlm_context* ctx, double* tflops) {
+    if (!ctx || !tflops) return fail(ctx, MLM_EINVAL, "mlm_fp64_peak: NULL argument");
+    DeviceGuard g(ctx->device);
+    int rc = ensure_dbuf(ctx, 64);
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream[0];
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    const int iters = 4096, blocks = ctx->sm_count * 8, threads = 256;
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        CK(cudaEventRecord(e0, st));
+        k_dfma_peak<<<blocks, threads, 0, st>>>((double*)ctx->dbuf, iters, 0.999999, 1e-7);
+        CK(cudaEventRecord(e1, st));
+        CK(cudaEventSynchronize(e1));
+        ctx->launches++;
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double flop = 2.0 * 64.0 * (double)iters * (double)blocks * (double)threads;
+        const double tf = flop / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    CK(cudaGetLastError());
+    *tflops = best;
+    return 0;
+}
+
+int mlm_kernel_info(mlm_context* ctx, int32_t* out, int n) {
+    if (!ctx || !out || n < 4) return fail(ctx, MLM_EINVAL, "mlm_kernel_info: bad argument");
+    DeviceGuard g(ctx->device);
+    cudaFuncAttributes a;
+    CK(cudaFuncGetAttributes(&a, (const void*)k_points<4>));
+    out[0] = a.numRegs;
+    out[1] = (int32_t)a.localSizeBytes;
+    CK(cudaFuncGetAttributes(&a, (const void*)k_map<4>));
+    out[2] = a.numRegs;
+    out[3] = (int32_t)a.localSizeBytes;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,64 @@
+// TEST-ONLY host build of the per-position device functions (mlm_core.cuh).
+// Lets the CPU test-suite check the kernel LOGIC (root finder, selection, Wirtinger
+// recursion) against the oracle without a GPU.  Never loaded by microlensing_b200.
+#ifdef MLM_STATS
+static long g_cnt_laguerre_evals = 0, g_cnt_newton_evals = 0;
+#define MLM_COUNT(name) (++g_cnt_##name)
+#endif
+#include "../../microlensing_b200/csrc/mlm_core.cuh"
+#include "../../microlensing_b200/csrc/mlm_qkl_generated.cuh"
+
+using namespace mlm;
+
+extern "C" {
+#ifdef MLM_STATS
+void emu_stats(long* out, int reset) { out[0] = g_cnt_laguerre_evals; out[1] = g_cnt_newton_evals; if (reset) g_cnt_laguerre_evals = g_cnt_newton_evals = 0; }
+#endif
+
+
+void emu_points(double s, double q, double rho, double Gamma, const double* zeta, long n, int order,
+                double* A0, double* A2, double* A4, unsigned char* nimg, unsigned char* flags) {
+    LensTable T;
+    make_table(s, q, &T);
+    SourceFactors sf = source_factors(rho, Gamma);
+    for (long i = 0; i < n; ++i) {
+        cd z = mk(zeta[2 * i], zeta[2 * i + 1]);
+        PointResult r = (order >= 4) ? point_magnification<4>(T, sf, z) : point_magnification<2>(T, sf, z);
+        A0[i] = r.A0; A2[i] = r.A2; A4[i] = r.A4;
+        nimg[i] = (unsigned char)r.nimg; flags[i] = (unsigned char)r.flags;
+    }
+}
+
+void emu_roots(double s, double q, const double* zeta, long n, double* roots, unsigned char* flags) {
+    LensTable T;
+    make_table(s, q, &T);
+    for (long i = 0; i < n; ++i) {
+        cd c[6], z[5];
+        unsigned fl = 0;
+        lens_polynomial(T, mk(zeta[2 * i], zeta[2 * i + 1]), c);
+        solve_roots(c, z, fl);
+        for (int k = 0; k < 5; ++k) { roots[10 * i + 2 * k] = z[k].x; roots[10 * i + 2 * k + 1] = z[k].y; }
+        flags[i] = (unsigned char)fl;
+    }
+}
+
+void emu_poly(double s, double q, const double* zeta, long n, double* coefs) {
+    LensTable T;
+    make_table(s, q, &T);
+    for (long i = 0; i < n; ++i) {
+        cd c[6];
+        lens_polynomial(T, mk(zeta[2 * i], zeta[2 * i + 1]), c);
+        for (int k = 0; k < 6; ++k) { coefs[12 * i + 2 * k] = c[k].x; coefs[12 * i + 2 * k + 1] = c[k].y; }
+    }
+}
+
+// per-image terms from W2..W6 (interleaved re,im; 5 complex per image)
+void emu_image_terms(const double* W, long n, int literal, double* mu) {
+    for (long i = 0; i < n; ++i) {
+        const double* w = W + 10 * i;
+        cd W2 = mk(w[0], w[1]), W3 = mk(w[2], w[3]), W4 = mk(w[4], w[5]), W5 = mk(w[6], w[7]), W6 = mk(w[8], w[9]);
+        ImageTerms t = literal ? image_terms_literal<4>(W2, W3, W4, W5, W6) : image_terms_from_W<4>(W2, W3, W4, W5, W6);
+        mu[3 * i] = t.mu0; mu[3 * i + 1] = t.mu2; mu[3 * i + 2] = t.mu4;
+    }
+}
+}

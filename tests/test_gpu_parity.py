@@ -1,0 +1,263 @@
+"""GPU parity tests: every call goes through the C ABI of libmlmultipoles.so (ctypes) and is compared
+with the oracle / the golden vectors of the live reference.  Tolerance: 1e-9 relative on A0/A2/A4
+(BASELINE.json north_star), image count exact, rules of tests/parity.py."""
+import io
+import contextlib
+
+import numpy as np
+import pytest
+
+import parity
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mb(built):
+    import microlensing_b200 as m
+    m._capi.context()           # fails loudly without a GPU / without the CUDA library
+    return m
+
+
+def truth_fn_factory(par, zeta):
+    from oracle.truth_mp import truth_point
+    return lambda i: truth_point(*par[i], zeta[i])
+
+
+def test_example_prints_reference_values(mb):
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        assert mb.multipoles.example() is None
+    got = buf.getvalue().splitlines()
+    ref = open("tests/golden/example_stdout.txt").read().splitlines()
+    assert len(got) == 4 and got[1] == ref[1] and got[3] == ref[3]
+    assert got[0].startswith(" A0, A2 =  ") and got[2].startswith(" A0, A2, A4 =  ")
+    for a, b in ((got[0], ref[0]), (got[2], ref[2])):
+        va = [float(x) for x in a.split("=")[1].split()]
+        vb = [float(x) for x in b.split("=")[1].split()]
+        assert va == pytest.approx(vb, rel=1e-9)
+    # the module is reachable the way the reference README says
+    from microlensing import multipoles
+    assert multipoles.example is mb.multipoles.example
+
+
+def test_golden_points(mb, golden_points):
+    g = golden_points
+    par, zeta = g["params"], g["zeta"]
+    n = len(zeta)
+    got_n, got_A, flags = np.zeros(n, int), np.zeros((n, 3)), np.zeros(n, int)
+    got_q = np.zeros((n, 2))
+    keys = {}
+    for i, p in enumerate(map(tuple, par)):
+        keys.setdefault(p, []).append(i)
+    for p, idx in keys.items():
+        idx = np.array(idx)
+        r = mb.magnification_points(*p, zeta[idx])
+        got_n[idx], flags[idx] = r["nimg"], r["flags"]
+        got_A[idx] = np.stack([r["A0"], r["A2"], r["A4"]], 1)
+        r2 = mb.magnification_points(*p, zeta[idx], order=2)
+        got_q[idx] = np.stack([r2["A0"], r2["A2"]], 1)
+        assert np.array_equal(r2["nimg"], r["nimg"]) and not r2["A4"].any()
+    mask = parity.mask_from_reference(g["hexadecapole"], g["residuals"], g["minJ"])
+    rep = parity.compare(got_n, got_A, g["nimg"], g["hexadecapole"], mask, truth_fn=truth_fn_factory(par, zeta))
+    print("golden parity:", rep)
+    assert (flags & 3).sum() == 0
+    # quadrupole path == first two outputs of the hexadecapole path (bit-identical in the reference)
+    assert np.array_equal(got_q, got_A[:, :2])
+    # against truth: rounding level, image counts exact
+    assert np.array_equal(got_n, g["truth_nimg"])
+    with np.errstate(all="ignore"):
+        rel = np.abs(got_A / g["truth"] - 1)
+    assert np.nanmax(rel) < 1e-11
+
+
+def test_direct_call_drop_ins(mb, golden_calls):
+    c = golden_calls
+    mp = mb.multipoles
+    off = 0
+    for k, n in enumerate(c["wk_n"]):
+        Wk = c["wk_flat"][off:off + 7 * n].reshape(7, n)
+        off += 7 * n
+        q2 = mp.quadrupole(Wk, c["wk_rho"][k], c["wk_gamma"][k])
+        h4 = mp.hexadecapole(Wk, c["wk_rho"][k], c["wk_gamma"][k])
+        assert q2.shape == (2,) and h4.shape == (3,) and q2.dtype == np.float64
+        assert np.allclose(q2, c["quad_out"][k], rtol=1e-9, atol=0), (k, n)
+        assert np.allclose(h4, c["hex_out"][k], rtol=1e-9, atol=0), (k, n)
+        if n == 0:
+            assert not h4.any() and not q2.any()
+    # rows 0-1 are never read: garbage there must not matter (np.empty in the reference, multipoles.py:186)
+    Wk = c["wk_flat"][:7 * 0 + 0]                              # (first entry has n=0); build a fresh one
+    rng = np.random.default_rng(3)
+    Wk = np.zeros((7, 5), complex)
+    Wk[2:] = 0.3 * (rng.normal(size=(5, 5)) + 1j * rng.normal(size=(5, 5)))
+    a = mp.hexadecapole(Wk, 0.01, 0.3)
+    Wk[:2] = np.nan
+    assert np.array_equal(mp.hexadecapole(Wk, 0.01, 0.3), a)
+    # a (7, 2, 3) table sums over every trailing axis (axis-less np.sum, multipoles.py:144-146)
+    assert np.allclose(mp.hexadecapole(Wk[:, :4].reshape(7, 2, 2), 0.01, 0.3),
+                       mp.hexadecapole(np.ascontiguousarray(Wk[:, :4]), 0.01, 0.3), rtol=1e-15)
+    with pytest.raises(IndexError):
+        mp.hexadecapole(np.zeros((5, 3), complex), 0.01, 0.)
+    # _akl
+    got = mp._akl(c["akl_mu"], c["akl_W2"], c["akl_Q"])
+    assert got.shape == c["akl_out"].shape
+    assert np.allclose(got, c["akl_out"], rtol=1e-14, atol=0)
+    assert np.allclose(mp._akl(2.0, 0.5 + 0.1j, 1 - 2j), 2.0 * (np.conj(1 - 2j) + np.conj(0.5 + 0.1j) * (1 - 2j)))
+    # _solvelenseq: same root set as np.roots (order unspecified)
+    for (s, q, z), ref in zip(c["solve_in"], c["solve_out"]):
+        got = mp._solvelenseq(s.real, q.real, z)
+        assert got.shape == (5,) and got.dtype == np.complex128
+        assert np.allclose(np.sort_complex(got), np.sort_complex(ref), rtol=0, atol=1e-9)
+    got = mp._solvelenseq(1.7, 0.2, np.complex128(-0.7833333333333334))
+    assert len(got) == 5
+    with pytest.raises(ValueError):
+        mp._solvelenseq(1.0, 0.5, np.array([0.1 + 0.1j, 0.2]))
+    assert len(mp._solvelenseq(1.0, 0.5, 0j)) == 4 and len(mp._solvelenseq(1.0, 0.5, -1 + 0j)) == 4
+
+
+@pytest.mark.parametrize("name,s,q,cx,half,nx", [("C4", 1.0, 0.5, -0.08, 0.80, 384), ("C3", 0.8, 0.1, 0.11, 0.75, 320)])
+def test_map_vs_batch_oracle(mb, name, s, q, cx, half, nx):
+    from oracle import cassan_oracle as oracle
+    rho, G = 1e-3, 0.5
+    ny = nx
+    x0, y0, dx, dy = cx - half, -half, 2 * half / nx, 2 * half / ny
+    m = mb.magnification_map(s, q, rho, G, x0, y0, dx, dy, nx, ny)
+    zeta = mb.map_coordinates(s, q, x0, y0, dx, dy, nx, ny)
+    nb, B0, B2, B4, z, keep, minJ, res = oracle.batch_a4(s, q, rho, G, zeta, return_extra=True)
+    ref_A = np.stack([B0.ravel(), B2.ravel(), B4.ravel()], 1)
+    mask = parity.mask_from_reference(ref_A, res, minJ.ravel())
+    got_A = np.stack([m["A0"].ravel(), m["A2"].ravel(), m["A4"].ravel()], 1)
+    zf = zeta.ravel()
+    par = [(s, q, rho, G)] * zf.size
+    rep = parity.compare(m["nimg"].ravel(), got_A, nb.ravel(), ref_A, mask, truth_fn=truth_fn_factory(par, zf))
+    print(name, "map parity:", rep, "f5 =", float((nb == 5).mean()))
+    assert rep["masked_frac"] < 0.01
+    assert (m["flags"] & 3).sum() == 0
+    # points API on the same coordinates gives bit-identical results (same per-thread arithmetic)
+    p = mb.magnification_points(s, q, rho, G, zeta)
+    for k in ("A0", "A2", "A4", "nimg", "flags"):
+        assert np.array_equal(p[k], m[k]), k
+
+
+def test_lightcurve_C2_vs_oracle(mb):
+    from oracle import cassan_oracle as oracle
+    s, q, rho, G = 1.0, 1e-3, 1e-3, 0.5
+    T = 20000
+    zeta = mb.lightcurve_coordinates(s, q, 0.01, 0.35, -2.0, 4.0 / T, T)
+    r = mb.magnification_points(s, q, rho, G, zeta)
+    nb, B0, B2, B4, z, keep, minJ, res = oracle.batch_a4(s, q, rho, G, zeta, return_extra=True)
+    ref_A = np.stack([B0, B2, B4], 1)
+    mask = parity.mask_from_reference(ref_A, res, minJ)
+    got_A = np.stack([r["A0"], r["A2"], r["A4"]], 1)
+    par = [(s, q, rho, G)] * T
+    rep = parity.compare(r["nimg"], got_A, nb, ref_A, mask, truth_fn=truth_fn_factory(par, zeta))
+    print("C2 parity:", rep)
+    # models API with M=1 reproduces the same light curve
+    mm = mb.magnification_models([s], [q], [rho], [G], [0.01], [0.35], -2.0, 4.0 / T, T)
+    assert np.array_equal(mm["nimg"][0], r["nimg"])
+    assert np.allclose(mm["A4"][0], r["A4"], rtol=1e-12)
+
+
+def test_models_C5_sample_vs_oracle(mb):
+    from oracle import cassan_oracle as oracle
+    rng = np.random.default_rng(20240517)
+    M, T = 24, 400
+    s = np.exp(rng.uniform(np.log(0.5), np.log(2.), M))
+    q = np.exp(rng.uniform(np.log(1e-4), np.log(1.), M))
+    rho = np.exp(rng.uniform(np.log(1e-4), np.log(1e-2), M))
+    G = np.full(M, 0.5)
+    u0, al = rng.uniform(-.5, .5, M), rng.uniform(0, 2 * np.pi, M)
+    r = mb.magnification_models(s, q, rho, G, u0, al, -2.0, 4.0 / T, T)
+    assert r["A4"].shape == (M, T)
+    got_n, got_A, ref_n, ref_A, masks, par, zs = [], [], [], [], [], [], []
+    for m in range(M):
+        zeta = mb.lightcurve_coordinates(s[m], q[m], u0[m], al[m], -2.0, 4.0 / T, T)
+        nb, B0, B2, B4, z, keep, minJ, res = oracle.batch_a4(s[m], q[m], rho[m], G[m], zeta, return_extra=True)
+        ra = np.stack([B0, B2, B4], 1)
+        ref_n.append(nb); ref_A.append(ra); masks.append(parity.mask_from_reference(ra, res, minJ))
+        got_n.append(r["nimg"][m]); got_A.append(np.stack([r["A0"][m], r["A2"][m], r["A4"][m]], 1))
+        par += [(s[m], q[m], rho[m], G[m])] * T
+        zs.append(zeta)
+    zs = np.concatenate(zs)
+    rep = parity.compare(np.concatenate(got_n), np.concatenate(got_A), np.concatenate(ref_n), np.concatenate(ref_A),
+                         np.concatenate(masks), truth_fn=truth_fn_factory(par, zs), max_adjudicate=1500)
+    print("C5 parity:", rep)
+
+
+def test_edge_cases(mb, golden_points):
+    s, q, rho, G = 1.0, 0.5, 1e-3, 0.5
+    z = np.array([0j, -1 + 0j, 1e-9 + 0j, 1e-6 + 1e-6j, -1 + 1e-8j, 50 + 20j])
+    r = mb.magnification_points(s, q, rho, G, z)
+    g = golden_points
+    m = np.where(g["tags"] == "edge")[0][:6]
+    assert np.array_equal(r["nimg"], g["nimg"][m])            # 3 images each, like the reference
+    assert np.allclose(np.stack([r["A0"], r["A2"], r["A4"]], 1), g["hexadecapole"][m], rtol=1e-9)
+    assert (r["flags"][:2] & 32).all()                         # degenerate polynomial reported
+    # empty and odd-sized inputs
+    e = mb.magnification_points(s, q, rho, G, np.zeros(0, complex))
+    assert e["A0"].shape == (0,)
+    one = mb.magnification_points(s, q, rho, G, 0.1 + 0.2j)
+    assert one["A4"].shape == () and one["nimg"][()] in (3, 5)
+    odd = mb.magnification_points(s, q, rho, G, np.full((3, 43), 0.1 + 0.2j))
+    assert odd["A4"].shape == (3, 43) and np.all(odd["A4"] == one["A4"][()])
+    em = mb.magnification_map(s, q, rho, G, -1., -1., 0.1, 0.1, 0, 0)
+    assert em["A0"].shape == (0, 0)
+    # argument errors surface as ValueError (negative return codes of the C ABI)
+    with pytest.raises(ValueError):
+        mb.magnification_points(-1.0, q, rho, G, z)
+    with pytest.raises(ValueError):
+        mb.magnification_points(s, q, rho, G, z, order=3)
+    # NaN input does not hang or crash: zero images
+    nn = mb.magnification_points(s, q, rho, G, np.array([complex(np.nan, 0.0)]))
+    assert nn["nimg"][0] == 0 and nn["A0"][0] == 0.0
+
+
+def test_row_sharding_is_bitwise_identical(mb):
+    """sharded results must equal single-GPU results bitwise."""
+    from microlensing_b200.sharding import shard_range
+    s, q, rho, G = 1.0, 0.5, 1e-3, 0.5
+    nx, ny = 256, 203
+    x0, y0, dx, dy = -0.88, -0.8, 1.6 / nx, 1.6 / ny
+    full = mb.magnification_map(s, q, rho, G, x0, y0, dx, dy, nx, ny)
+    for world in (2, 3, 8):
+        parts = []
+        for r in range(world):
+            lo, hi = shard_range(ny, r, world)
+            parts.append(mb.magnification_map(s, q, rho, G, x0, y0, dx, dy, nx, ny, row0=lo, nrows=hi - lo))
+        for k in ("A0", "A2", "A4", "nimg", "flags"):
+            assert np.array_equal(np.concatenate([p[k] for p in parts], 0), full[k]), (world, k)
+
+
+def test_device_pointer_api_and_sharded_map(mb):
+    import torch
+    from microlensing_b200.sharding import ShardedMap
+    s, q, rho, G = 0.8, 0.1, 1e-3, 0.5
+    nx = ny = 192
+    x0, y0, dx, dy = 0.11 - 0.75, -0.75, 1.5 / nx, 1.5 / ny
+    sm = ShardedMap(nx, ny, 0, 1, nchunks=3)
+    sm.compute(s, q, rho, G, x0, y0, dx, dy)
+    torch.cuda.synchronize()
+    dev = sm.assemble_host()
+    host = mb.magnification_map(s, q, rho, G, x0, y0, dx, dy, nx, ny)
+    for k in ("A0", "A2", "A4", "nimg", "flags"):
+        assert np.array_equal(dev[k], host[k]), k
+
+
+def test_full_size_properties(mb):
+    """BASELINE sizes through size-independent properties: the lens is symmetric about the real
+    axis, so a map whose window is symmetric in y equals its own vertical mirror; image counts are
+    3 or 5; A0 >= 1 (total point-source magnification of a binary lens)."""
+    s, q, rho, G = 1.0, 0.5, 1e-3, 0.5
+    nx, ny = 8192, 1024                      # 8192-wide rows of the headline map, both central bands
+    half = 0.8
+    x0, dx, dy = -0.08 - half, 2 * half / 8192, 2 * half / 8192
+    top = mb.magnification_map(s, q, rho, G, x0, -half, dx, dy, nx, 8192, row0=4096 - ny, nrows=ny)
+    bot = mb.magnification_map(s, q, rho, G, x0, -half, dx, dy, nx, 8192, row0=4096, nrows=ny)
+    assert np.array_equal(top["nimg"], bot["nimg"][::-1])
+    for k in ("A0", "A2", "A4"):
+        assert np.allclose(top[k], bot[k][::-1], rtol=1e-11, atol=0), k
+    assert set(np.unique(top["nimg"])) <= {3, 5}
+    assert top["A0"].min() >= 1.0
+    assert ((top["flags"] & 3) == 0).all()
+    f5 = float((top["nimg"] == 5).mean())
+    assert 0.05 < f5 < 0.6
