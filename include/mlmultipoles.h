@@ -13,7 +13,7 @@
  *  - every function returns 0 on success, a negative MLM_E* code for argument errors, or a
  *    positive cudaError_t; mlm_last_error() gives the message; nothing throws;
  *  - the caller owns every buffer.  Un-suffixed functions take DEVICE pointers and enqueue
- *    on `stream` (a cudaStream_t passed as void*, NULL = the context's own stream) without
+ *    on `stream` (a cudaStream_t passed as void*, NULL = the CUDA default stream) without
  *    synchronising; *_host functions take HOST pointers, copy in/out themselves and return
  *    when the results are in the host buffers;
  *  - frames: `zeta` arguments are in the PRIMARY-LENS frame (primary mass 1/(1+q) at 0,

@@ -66,8 +66,8 @@ def magnification_points(s, q, rho, Gamma, zeta, order=4, out=None, device=None)
     Per position this is the body of example(), multipoles.py:181-202.
     """
     ctx = _capi.context(device)
-    zeta = np.ascontiguousarray(zeta, dtype=np.complex128)
-    shape = zeta.shape
+    shape = np.shape(zeta)
+    zeta = np.ascontiguousarray(zeta, dtype=np.complex128).reshape(shape)   # ascontiguousarray makes 0-d into 1-d
     if out is None:
         out = alloc_outputs(shape, device, pinned=zeta.size >= (1 << 16))
     _check_out(out, shape)

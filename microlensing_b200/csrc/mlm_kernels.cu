@@ -244,8 +244,11 @@ static int ensure_dbuf(mlm_context* ctx, size_t bytes) {
     return 0;
 }
 
+// NULL is the CUDA default stream (what torch.cuda.current_stream().cuda_stream is unless the
+// caller switched streams), like every CUDA library API.
 static inline cudaStream_t pick(mlm_context* ctx, void* stream) {
-    return stream ? (cudaStream_t)stream : ctx->stream[0];
+    (void)ctx;
+    return (cudaStream_t)stream;
 }
 
 static bool bad_lens(double s, double q) { return !(s > 0.0) || !(q > 0.0) || !std::isfinite(s) || !std::isfinite(q); }
