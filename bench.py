@@ -318,7 +318,7 @@ def bench_b200(args):
     flag_any = float((sm.local["flags"][: sm.plan.nrows * nx] != 0).sum())
 
     # ---- end to end through the public host API ---------------------------------------------------
-    lo, hi = shard_range(ny, rank, world)
+    lo, hi = shard_range(ny, rank, world, sm.align)
     out = mb.alloc_outputs((hi - lo, nx), device=local, pinned=True)
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     mb.magnification_map(s, q, rho, G, x0, y0, dx, dy, nx, ny, row0=lo, nrows=hi - lo, out=out, device=local)

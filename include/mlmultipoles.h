@@ -61,6 +61,9 @@ int mlm_synchronize(mlm_context* ctx);
 int mlm_alloc_host(mlm_context* ctx, int64_t bytes, void** out);
 int mlm_free_host(mlm_context* ctx, void* p);
 
+/* rows per warm-start strip of mlm_map (default 32; env MLM_MAP_STRIP at mlm_create) */
+int mlm_map_strip(mlm_context* ctx);
+
 /* ---- the fused path: replaces the per-position body of example(), multipoles.py:181-202
  *      (_solvelenseq :156-165, selection :182-183, Wk :185-201, hexadecapole :67-148) -------- */
 
@@ -75,7 +78,10 @@ int mlm_points_host(mlm_context* ctx, double s, double q, double rho, double Gam
 /* Magnification map: pixel (row r, column c) has centre-of-mass source position
  *   x = x0 + (c + 0.5) dx,  y = y0 + (r + 0.5) dy          (generated in the kernel),
  * rows [row0, row0 + nrows) of an nx-wide map are written to out[(r - row0) * nx + c]
- * (row-shardable: "... to be computed for all source center positions", multipoles.py:184). */
+ * (row-shardable: "... to be computed for all source center positions", multipoles.py:184).
+ * Rows are processed in strips of mlm_map_strip() consecutive rows (aligned to absolute row
+ * numbers) with warm-started root tracking inside a strip: shards whose row0 is a multiple of
+ * the strip length reproduce the unsharded map bit for bit. */
 int mlm_map(mlm_context* ctx, double s, double q, double rho, double Gamma,
             double x0, double y0, double dx, double dy, int64_t nx, int64_t row0, int64_t nrows, int order,
             double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags, void* stream);

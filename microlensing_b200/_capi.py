@@ -13,7 +13,7 @@ import weakref
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmlmultipoles.so")
+LIB_PATH = os.environ.get("MLM_LIB") or os.path.join(_HERE, "libmlmultipoles.so")   # MLM_LIB: experiments only
 
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_u8_p = ctypes.POINTER(ctypes.c_uint8)
@@ -25,6 +25,7 @@ SIGNATURES = {
     "mlm_destroy": [_P],
     "mlm_launch_count": [_P, ctypes.POINTER(_L)],
     "mlm_synchronize": [_P],
+    "mlm_map_strip": [_P],
     "mlm_alloc_host": [_P, _L, ctypes.POINTER(_P)],
     "mlm_free_host": [_P, _P],
     "mlm_points": [_P, _D, _D, _D, _D, _P, _L, _I, _P, _P, _P, _P, _P, _P],

@@ -189,6 +189,10 @@ MLM_HD void lens_polynomial(const LensTable& T, cd zeta, cd c[6]) {
 #endif
 #define MLM_EPS 1.1102230246251565e-16               /* 2^-53 */
 #define MLM_LAG_MAXIT 64
+// Newton on the quintic stops once a step is below 1e-6 |z|: by quadratic convergence the root is
+// then good to ~K 1e-12 |z| (K = |p''/2p'|), enough for the 1e-6 residual test; the physical
+// images are subsequently polished on the lens equation itself to rounding level.
+#define MLM_NEWTON_TOL2 1e-12
 #ifndef MLM_FLAG_NOCONV          /* same values as include/mlmultipoles.h */
 #define MLM_FLAG_NOCONV 1        /* an iteration cap was hit */
 #define MLM_FLAG_VIETE 2         /* reserved */
@@ -326,13 +330,82 @@ MLM_HD int solve_roots(const cd c[6], cd z[5], unsigned& flags) {
                 const double dz2 = norm2(dz);
                 if (!(dz2 < 1e300)) break;            // p'=0 or overflow: keep the deflated root
                 zk = zk - dz;
-                if (dz2 <= 1e-18 * norm2(zk)) break;  // quadratic: next step would be < 1e-18 |z|
+                if (dz2 <= MLM_NEWTON_TOL2 * norm2(zk)) break;
                 if (j == 3) flags |= MLM_FLAG_NOCONV;
             }
             z[k] = zk;
         }
     }
     return deg0;
+}
+
+// Warm start: the five roots of a NEIGHBOURING source position (previous map row / previous
+// epoch) are carried into the new polynomial by Newton iterations on the full quintic, which
+// replaces the ~14 Laguerre iterations of the cold solve by ~3 Newton steps per root.
+// Returns false -- the caller then falls back to solve_roots() -- unless every iteration
+// converged and the five results are five DISTINCT roots (Vieta: sum z_k = -c4/c5; two tracks
+// collapsing onto one root, the failure mode next to a caustic, breaks the sum by their
+// separation).  The accepted roots satisfy the same stopping rule as the cold path's polish.
+MLM_HD bool track_roots(const cd c[6], cd z[5]) {
+    if (c[5].x == 0.0 && c[5].y == 0.0) return false;
+    bool ok = true;
+    cd sum = mk(0.0, 0.0);
+    double mag = 1.0;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        cd zk = z[k];
+        bool conv = false;
+#pragma unroll 1
+        for (int j = 0; j < 6; ++j) {
+            cd p, dp;
+            horner2(c, zk, p, dp);
+            MLM_COUNT(newton_evals);
+            const cd dz = cmul(p, crcp(dp));
+            const double dz2 = norm2(dz);
+            if (!(dz2 < 1e300)) break;
+            zk = zk - dz;
+            if (dz2 <= MLM_NEWTON_TOL2 * norm2(zk)) { conv = true; break; }
+        }
+        ok = ok && conv;
+        z[k] = zk;
+        sum = sum + zk;
+        mag += norm2(zk);
+    }
+    const cd v = cfma(c[4], crcp(c[5]), sum);
+    return ok && (norm2(v) <= 1e-16 * mag);
+}
+
+// One step of a coherent sequence of source positions (map column, light curve): bring the
+// root store (current roots sz[k*stride], previous roots szp[k*stride]; shared memory in the
+// kernels) to the new polynomial c.  hist = number of usable earlier positions (0: cold start,
+// 1: warm start from sz, 2: warm start from the linear extrapolation 2 sz - szp, which cuts the
+// initial error from O(h) to O(h^2) and the Newton work to ~1 step per root).  Falls back to
+// the cold solve whenever tracking is rejected.  Returns the new hist.
+MLM_HD int advance_roots(const cd c[6], cd* sz, cd* szp, int stride, int hist, unsigned& flags) {
+    cd z[5];
+    if (hist >= 1) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const cd zc = sz[k * stride];
+            cd pred = zc;
+            if (hist >= 2) {
+                const cd zo = szp[k * stride];
+                pred = mk(fma(2.0, zc.x, -zo.x), fma(2.0, zc.y, -zo.y));
+            }
+            szp[k * stride] = zc;
+            z[k] = pred;
+        }
+        if (track_roots(c, z)) {
+#pragma unroll
+            for (int k = 0; k < 5; ++k) sz[k * stride] = z[k];
+            return 2;
+        }
+        MLM_COUNT(track_fallbacks);
+    }
+    const int deg = solve_roots(c, z, flags);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) sz[k * stride] = z[k];
+    return deg == 5 ? 1 : 0;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -450,19 +523,16 @@ struct PointResult {
 // (c)+(d)+(e): given the polynomial roots, select the physical images, polish them on the
 // lens equation itself, and accumulate A0/A2/A4.
 template <int ORDER>
-MLM_HD void accumulate_images(const LensTable& T, const SourceFactors sf, cd zeta, const cd z[5],
+MLM_HD void accumulate_images(const LensTable& T, const SourceFactors sf, cd zeta, const cd* z, int zstride,
                               PointResult& out) {
     double A0 = 0.0, A2 = 0.0, A4 = 0.0, minJ = 1e300;
     unsigned n = 0, flags = out.flags;
     // The image loop is kept rolled (5 x ~500 instructions would overflow the instruction
-    // cache); the roots rotate through zr[0] so that no register array is indexed dynamically.
-    cd zr[5];
-#pragma unroll
-    for (int k = 0; k < 5; ++k) zr[k] = z[k];
+    // cache); the roots are read from memory (shared memory in the kernels) with stride zstride,
+    // so no register array is indexed dynamically and they occupy no registers meanwhile.
 #pragma unroll 1
     for (int k = 0; k < 5; ++k) {
-        cd zk = zr[0];
-        zr[0] = zr[1]; zr[1] = zr[2]; zr[2] = zr[3]; zr[3] = zr[4];
+        cd zk = z[k * zstride];
         cd zs = mk(zk.x + T.s, zk.y);
         cd r1 = crcp(zk), r2 = crcp(zs);
         // residual of the lens equation, multipoles.py:182-183
@@ -471,10 +541,11 @@ MLM_HD void accumulate_images(const LensTable& T, const SourceFactors sf, cd zet
         const double f2 = norm2(f);
         if (f2 > 1e-14 && f2 < 1e-10) flags |= MLM_FLAG_AMBIG;
         if (!(f2 < 1e-8)) continue;                   // NaN residual -> rejected, like NumPy
-        // One Newton step on the lens equation z - zeta - conj(W1(z)) = 0 (well conditioned,
-        // unlike the polynomial at small q):  dz = -(f + conj(W2) conj(f)) / (1 - |W2|^2)
+        // Newton on the lens equation z - zeta - conj(W1(z)) = 0 (well conditioned, unlike the
+        // polynomial at small q):  dz = -(f + conj(W2) conj(f)) / (1 - |W2|^2)
         bool phys = (f2 < 1e-12);                     // the reference's test, multipoles.py:183
-        {
+#pragma unroll 1
+        for (int it = 0; it < 2; ++it) {
             const cd r1s = csq(r1), r2s = csq(r2);
             const cd W2 = rfma(T.alpha[2], r1s, scale(T.beta[2], r2s));
             const double iJ = rcp(1.0 - norm2(W2));
@@ -484,16 +555,19 @@ MLM_HD void accumulate_images(const LensTable& T, const SourceFactors sf, cd zet
             // noise of an ill-conditioned polynomial, amplified by |W2| >> 1 (faint image next
             // to a low-mass lens), can push a true image over the threshold; it is kept iff a
             // minute Newton step (< 1e-8) lands on an exact solution.
-            if (dz2 < (phys ? 1e-10 : 1e-16)) {
-                zk = zk + dz;
-                zs = mk(zk.x + T.s, zk.y);
-                r1 = crcp(zk);
-                r2 = crcp(zs);
-                if (!phys) {
-                    W1 = rfma(T.alpha[1], r1, scale(T.beta[1], r2));
-                    f = zk - zeta - conj(W1);
-                    phys = (norm2(f) < 1e-18);
-                }
+            if (!(dz2 < (phys ? 1e-10 : 1e-16))) break;
+            zk = zk + dz;
+            zs = mk(zk.x + T.s, zk.y);
+            r1 = crcp(zk);
+            r2 = crcp(zs);
+            // a second step only when the first one was not already below 1e-10 |z| (its
+            // quadratic remainder could then exceed rounding) or the root is being rescued
+            if (phys && dz2 <= 1e-20 * norm2(zk)) break;
+            W1 = rfma(T.alpha[1], r1, scale(T.beta[1], r2));
+            f = zk - zeta - conj(W1);
+            if (!phys) {
+                phys = (norm2(f) < 1e-18);
+                break;
             }
         }
         if (!phys) continue;
@@ -532,7 +606,7 @@ MLM_HD PointResult point_magnification(const LensTable& T, const SourceFactors s
     out.flags = 0;
     lens_polynomial(T, zeta, c);
     solve_roots(c, z, out.flags);
-    accumulate_images<ORDER>(T, sf, zeta, z, out);
+    accumulate_images<ORDER>(T, sf, zeta, z, 1, out);
     return out;
 }
 

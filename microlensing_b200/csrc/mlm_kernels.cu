@@ -25,6 +25,9 @@
 using namespace mlm;
 
 #define MLM_BLOCK 128
+#ifndef MLM_MAP_MINBLOCKS
+#define MLM_MAP_MINBLOCKS 3          /* k_map: <= 168 registers -> 3 blocks (12 warps) per SM, no spill */
+#endif
 
 // ------------------------------------------------------------------------------------------
 // kernels
@@ -48,26 +51,56 @@ k_points(const __grid_constant__ LensTable T, const SourceFactors sf, const doub
     const int64_t i = (int64_t)blockIdx.x * MLM_BLOCK + threadIdx.x;
     if (i >= n) return;
     const double2 zz = __ldg(zeta + i);               // one 16-byte load per thread, coalesced
-    const PointResult r = point_magnification<ORDER>(T, sf, mk(zz.x, zz.y));
+    __shared__ cd s_roots[5][MLM_BLOCK];
+    cd* const sz = &s_roots[0][threadIdx.x];
+    const cd zt = mk(zz.x, zz.y);
+    cd c[6];
+    PointResult r;
+    r.flags = 0;
+    lens_polynomial(T, zt, c);
+    advance_roots(c, sz, sz, MLM_BLOCK, 0, r.flags);  // hist = 0: cold solve
+    accumulate_images<ORDER>(T, sf, zt, sz, MLM_BLOCK, r);
     store_result(r, i, A0, A2, A4, nimg, flags);
 }
 
 // K1b: magnification map, zeta generated in-kernel (no input traffic).
-// blockIdx.x tiles the columns, blockIdx.y strides over the rows of this shard.
+// blockIdx.x tiles the columns; blockIdx.y strides over STRIPS of `strip` consecutive rows
+// (aligned to absolute row numbers, so any row-sharding on multiples of `strip` reproduces the
+// single-GPU arithmetic bit for bit).  A thread walks down its column inside the strip: the
+// first row is a cold solve (Laguerre + deflation), every further row warm-starts Newton from
+// the roots of the row above (pixel pitch ~2e-4 theta_E) and falls back to the cold solve when
+// the tracking check fails (next to caustics).  Stores are coalesced across the 128 columns.
 template <int ORDER>
-__global__ void __launch_bounds__(MLM_BLOCK)
+__global__ void __launch_bounds__(MLM_BLOCK, MLM_MAP_MINBLOCKS)
 k_map(const __grid_constant__ LensTable T, const SourceFactors sf, double x0, double y0, double dx, double dy,
-      double shift, int64_t nx, int64_t row0, int64_t nrows, double* __restrict__ A0, double* __restrict__ A2,
-      double* __restrict__ A4, uint8_t* __restrict__ nimg, uint8_t* __restrict__ flags) {
+      double shift, int64_t nx, int64_t row0, int64_t nrows, int strip, double* __restrict__ A0,
+      double* __restrict__ A2, double* __restrict__ A4, uint8_t* __restrict__ nimg, uint8_t* __restrict__ flags) {
+    // root store of this thread: current and previous roots, [k][thread] so that a warp touches
+    // 512 contiguous bytes per k (conflict-free); keeps 20 doubles out of the register file
+    __shared__ cd s_roots[2][5][MLM_BLOCK];
+    cd* const sz = &s_roots[0][0][threadIdx.x];
+    cd* const szp = &s_roots[1][0][threadIdx.x];
     const int64_t col = (int64_t)blockIdx.x * MLM_BLOCK + threadIdx.x;
     if (col >= nx) return;
     // x = x0 + (col + 0.5) dx with two roundings (no FMA), so that host code can reproduce
     // the coordinates bit for bit with the same expression.
     const double x = __dadd_rn(__dadd_rn(x0, __dmul_rn((double)col + 0.5, dx)), -shift);
-    for (int64_t r = blockIdx.y; r < nrows; r += gridDim.y) {
-        const double y = __dadd_rn(y0, __dmul_rn((double)(row0 + r) + 0.5, dy));
-        const PointResult res = point_magnification<ORDER>(T, sf, mk(x, y));
-        store_result(res, r * nx + col, A0, A2, A4, nimg, flags);
+    const int64_t k_first = row0 / strip, k_last = (row0 + nrows - 1) / strip;
+    for (int64_t k = k_first + blockIdx.y; k <= k_last; k += gridDim.y) {
+        const int64_t ra = (k * strip > row0) ? k * strip : row0;
+        const int64_t rb = ((k + 1) * strip < row0 + nrows) ? (k + 1) * strip : row0 + nrows;
+        int hist = 0;
+        for (int64_t r = ra; r < rb; ++r) {
+            const double y = __dadd_rn(y0, __dmul_rn((double)r + 0.5, dy));
+            const cd zeta = mk(x, y);
+            cd c[6];
+            PointResult res;
+            res.flags = 0;
+            lens_polynomial(T, zeta, c);
+            hist = advance_roots(c, sz, szp, MLM_BLOCK, hist, res.flags);
+            accumulate_images<ORDER>(T, sf, zeta, sz, MLM_BLOCK, res);
+            store_result(res, (r - row0) * nx + col, A0, A2, A4, nimg, flags);
+        }
     }
 }
 
@@ -202,6 +235,7 @@ struct mlm_context {
     std::atomic<int64_t> launches{0};
     std::string err;
     int sm_count = 148;
+    int map_strip = 32;                                // rows per warm-start strip of k_map (MLM_MAP_STRIP)
 };
 
 static std::string g_err;
@@ -285,6 +319,10 @@ int mlm_create(int device, mlm_context** out) {
         }
     }
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (const char* e2 = getenv("MLM_MAP_STRIP")) {
+        const int v = atoi(e2);
+        if (v >= 1 && v <= 4096) ctx->map_strip = v;
+    }
     *out = ctx;
     return 0;
 }
@@ -308,6 +346,8 @@ int mlm_launch_count(mlm_context* ctx, int64_t* out) {
     *out = ctx->launches.load();
     return 0;
 }
+
+int mlm_map_strip(mlm_context* ctx) { return ctx ? ctx->map_strip : MLM_EINVAL; }
 
 int mlm_synchronize(mlm_context* ctx) {
     if (!ctx) return fail(ctx, MLM_EINVAL, "mlm_synchronize: NULL context");
@@ -369,12 +409,14 @@ int mlm_map(mlm_context* ctx, double s, double q, double rho, double Gamma, doub
     make_table(s, q, &T);
     const SourceFactors sf = source_factors(rho, Gamma);
     const double shift = s * q / (1.0 + q);            // multipoles.py:178
-    dim3 grid((unsigned)((nx + MLM_BLOCK - 1) / MLM_BLOCK), (unsigned)(nrows < 65535 ? nrows : 65535));
+    const int strip = ctx->map_strip;
+    const int64_t nstrips = (row0 + nrows - 1) / strip - row0 / strip + 1;
+    dim3 grid((unsigned)((nx + MLM_BLOCK - 1) / MLM_BLOCK), (unsigned)(nstrips < 65535 ? nstrips : 65535));
     cudaStream_t st = pick(ctx, stream);
     if (order == 4)
-        k_map<4><<<grid, MLM_BLOCK, 0, st>>>(T, sf, x0, y0, dx, dy, shift, nx, row0, nrows, A0, A2, A4, nimg, flags);
+        k_map<4><<<grid, MLM_BLOCK, 0, st>>>(T, sf, x0, y0, dx, dy, shift, nx, row0, nrows, strip, A0, A2, A4, nimg, flags);
     else
-        k_map<2><<<grid, MLM_BLOCK, 0, st>>>(T, sf, x0, y0, dx, dy, shift, nx, row0, nrows, A0, A2, A4, nimg, flags);
+        k_map<2><<<grid, MLM_BLOCK, 0, st>>>(T, sf, x0, y0, dx, dy, shift, nx, row0, nrows, strip, A0, A2, A4, nimg, flags);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;

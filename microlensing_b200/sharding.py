@@ -18,13 +18,21 @@ __all__ = ["shard_range", "ShardPlan", "plan_map", "BYTES_PER_POSITION", "Sharde
 BYTES_PER_POSITION = 26           # 3 x float64 + 2 x uint8
 
 
-def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
-    """Contiguous block [lo, hi) of n units for `rank`; the first n % world ranks get one more."""
-    if world <= 0 or not (0 <= rank < world) or n < 0:
+MAP_STRIP = 32                    # default rows per warm-start strip of the map kernel (mlm_map_strip)
+
+
+def shard_range(n: int, rank: int, world: int, align: int = 1) -> tuple[int, int]:
+    """Contiguous block [lo, hi) of n units for `rank`; the first ranks get the remainder.
+
+    With align > 1 the boundaries are multiples of `align` (map shards start on a strip boundary
+    of the map kernel, which makes sharded == unsharded bit for bit)."""
+    if world <= 0 or not (0 <= rank < world) or n < 0 or align < 1:
         raise ValueError("bad shard arguments")
-    base, extra = divmod(n, world)
+    nb = -(-n // align)
+    base, extra = divmod(nb, world)
     lo = rank * base + min(rank, extra)
-    return lo, lo + base + (1 if rank < extra else 0)
+    hi = lo + base + (1 if rank < extra else 0)
+    return min(lo * align, n), min(hi * align, n)
 
 
 @dataclass(frozen=True)
@@ -37,17 +45,18 @@ class ShardPlan:
     chunks: tuple                 # ((row offset within shard, rows), ...) pipelining units
 
 
-def plan_map(ny: int, rank: int, world: int, nchunks: int = 4) -> ShardPlan:
-    lo, hi = shard_range(ny, rank, world)
-    max_rows = shard_range(ny, 0, world)[1]
+def plan_map(ny: int, rank: int, world: int, nchunks: int = 4, align: int = MAP_STRIP) -> ShardPlan:
+    lo, hi = shard_range(ny, rank, world, align)
+    max_rows = shard_range(ny, 0, world, align)[1]
     n = hi - lo
     # chunk boundaries come from max_rows so that they are identical on every rank (the gather
     # needs equal sizes); a rank with fewer rows computes only the rows it owns in each chunk
     nchunks = max(1, min(nchunks, max_rows)) if max_rows else 1
     chunks = []
     for c in range(nchunks):
-        a, b = shard_range(max_rows, c, nchunks)
-        chunks.append((a, b - a))
+        a, b = shard_range(max_rows, c, nchunks, align)
+        if b > a:
+            chunks.append((a, b - a))
     return ShardPlan(rank, world, lo, n, max_rows, tuple(chunks))
 
 
@@ -61,11 +70,13 @@ class ShardedMap:
     overlapping the next chunk's kernel.
     """
 
-    def __init__(self, nx: int, ny: int, rank: int = 0, world: int = 1, device=None, nchunks: int = 4, group=None):
+    def __init__(self, nx: int, ny: int, rank: int = 0, world: int = 1, device=None, nchunks: int = 4, group=None,
+                 align: int = MAP_STRIP):
         import torch
         self.torch = torch
         self.nx, self.ny = nx, ny
-        self.plan = plan_map(ny, rank, world, nchunks)
+        self.align = align
+        self.plan = plan_map(ny, rank, world, nchunks, align)
         self.group = group
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         n_slot = self.plan.max_rows * nx
@@ -124,7 +135,7 @@ class ShardedMap:
         for key in ("A0", "A2", "A4", "nimg", "flags"):
             parts = []
             for r in range(p.world):
-                lo, hi = shard_range(self.ny, r, p.world)
+                lo, hi = shard_range(self.ny, r, p.world, self.align)
                 src = self.local if (p.world == 1 or r == 0) else self.full[r]
                 parts.append(src[key][:(hi - lo) * nx].cpu().numpy().reshape(hi - lo, nx))
             out[key] = np.concatenate(parts, axis=0)

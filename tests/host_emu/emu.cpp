@@ -2,7 +2,7 @@
 // Lets the CPU test-suite check the kernel LOGIC (root finder, selection, Wirtinger
 // recursion) against the oracle without a GPU.  Never loaded by microlensing_b200.
 #ifdef MLM_STATS
-static long g_cnt_laguerre_evals = 0, g_cnt_newton_evals = 0;
+static long g_cnt_laguerre_evals = 0, g_cnt_newton_evals = 0, g_cnt_track_fallbacks = 0;
 #define MLM_COUNT(name) (++g_cnt_##name)
 #endif
 #include "../../microlensing_b200/csrc/mlm_core.cuh"
@@ -61,4 +61,31 @@ void emu_image_terms(const double* W, long n, int literal, double* mu) {
         mu[3 * i] = t.mu0; mu[3 * i + 1] = t.mu2; mu[3 * i + 2] = t.mu4;
     }
 }
+}
+
+// column strip of a map with warm-started tracking, same control flow as k_map
+extern "C" void emu_strip(double s, double q, double rho, double Gamma, const double* zeta, long n, int strip,
+                          double* A0, double* A2, double* A4, unsigned char* nimg, unsigned char* flags,
+                          long* ncold) {
+    LensTable T;
+    make_table(s, q, &T);
+    SourceFactors sf = source_factors(rho, Gamma);
+    cd z[5], zp[5];
+    int hist = 0;
+    long cold = 0;
+    for (long i = 0; i < n; ++i) {
+        if (i % strip == 0) hist = 0;
+        cd zeta_i = mk(zeta[2 * i], zeta[2 * i + 1]);
+        cd c[6];
+        PointResult r;
+        r.flags = 0;
+        lens_polynomial(T, zeta_i, c);
+        const int before = hist;
+        hist = advance_roots(c, z, zp, 1, hist, r.flags);
+        if (before == 0 || hist < 2) ++cold;
+        accumulate_images<4>(T, sf, zeta_i, z, 1, r);
+        A0[i] = r.A0; A2[i] = r.A2; A4[i] = r.A4;
+        nimg[i] = (unsigned char)r.nimg; flags[i] = (unsigned char)r.flags;
+    }
+    *ncold = cold;
 }

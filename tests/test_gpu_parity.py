@@ -19,6 +19,18 @@ def mb(built):
     return m
 
 
+def match_root_sets(a, b):
+    """max distance after greedy nearest-neighbour pairing of two unordered root sets"""
+    b = list(b)
+    worst = 0.0
+    for z in a:
+        d = [abs(z - w) for w in b]
+        k = int(np.argmin(d))
+        worst = max(worst, d[k])
+        b.pop(k)
+    return worst
+
+
 def truth_fn_factory(par, zeta):
     from oracle.truth_mp import truth_point
     return lambda i: truth_point(*par[i], zeta[i])
@@ -107,7 +119,7 @@ def test_direct_call_drop_ins(mb, golden_calls):
     for (s, q, z), ref in zip(c["solve_in"], c["solve_out"]):
         got = mp._solvelenseq(s.real, q.real, z)
         assert got.shape == (5,) and got.dtype == np.complex128
-        assert np.allclose(np.sort_complex(got), np.sort_complex(ref), rtol=0, atol=1e-9)
+        assert match_root_sets(got, ref) < 1e-9
     got = mp._solvelenseq(1.7, 0.2, np.complex128(-0.7833333333333334))
     assert len(got) == 5
     with pytest.raises(ValueError):
@@ -133,10 +145,14 @@ def test_map_vs_batch_oracle(mb, name, s, q, cx, half, nx):
     print(name, "map parity:", rep, "f5 =", float((nb == 5).mean()))
     assert rep["masked_frac"] < 0.01
     assert (m["flags"] & 3).sum() == 0
-    # points API on the same coordinates gives bit-identical results (same per-thread arithmetic)
+    # points API (cold root solve per position) vs the map kernel (warm-started tracking down the
+    # columns): same roots up to the Newton stopping rule -> identical image counts, values at
+    # rounding level (amplified next to caustics, where the mask applies)
     p = mb.magnification_points(s, q, rho, G, zeta)
-    for k in ("A0", "A2", "A4", "nimg", "flags"):
-        assert np.array_equal(p[k], m[k]), k
+    assert np.array_equal(p["nimg"], m["nimg"])
+    for k in ("A0", "A2", "A4"):
+        rel = np.abs(p[k] / m[k] - 1)
+        assert rel[~mask.reshape(rel.shape)].max() < 1e-10, k
 
 
 def test_lightcurve_C2_vs_oracle(mb):
@@ -219,13 +235,20 @@ def test_row_sharding_is_bitwise_identical(mb):
     nx, ny = 256, 203
     x0, y0, dx, dy = -0.88, -0.8, 1.6 / nx, 1.6 / ny
     full = mb.magnification_map(s, q, rho, G, x0, y0, dx, dy, nx, ny)
+    strip = mb._capi.context().lib.mlm_map_strip(mb._capi.context().handle)
+    assert strip == 32
     for world in (2, 3, 8):
         parts = []
         for r in range(world):
-            lo, hi = shard_range(ny, r, world)
+            lo, hi = shard_range(ny, r, world, align=strip)        # shards start on strip boundaries
             parts.append(mb.magnification_map(s, q, rho, G, x0, y0, dx, dy, nx, ny, row0=lo, nrows=hi - lo))
         for k in ("A0", "A2", "A4", "nimg", "flags"):
             assert np.array_equal(np.concatenate([p[k] for p in parts], 0), full[k]), (world, k)
+    # unaligned shards still agree to rounding (a strip cut in two starts with one more cold solve)
+    a = mb.magnification_map(s, q, rho, G, x0, y0, dx, dy, nx, ny, row0=0, nrows=50)
+    b = mb.magnification_map(s, q, rho, G, x0, y0, dx, dy, nx, ny, row0=50, nrows=ny - 50)
+    assert np.array_equal(np.concatenate([a["nimg"], b["nimg"]], 0), full["nimg"])
+    assert np.allclose(np.concatenate([a["A4"], b["A4"]], 0), full["A4"], rtol=1e-9, atol=0)
 
 
 def test_device_pointer_api_and_sharded_map(mb):
@@ -254,8 +277,14 @@ def test_full_size_properties(mb):
     top = mb.magnification_map(s, q, rho, G, x0, -half, dx, dy, nx, 8192, row0=4096 - ny, nrows=ny)
     bot = mb.magnification_map(s, q, rho, G, x0, -half, dx, dy, nx, 8192, row0=4096, nrows=ny)
     assert np.array_equal(top["nimg"], bot["nimg"][::-1])
+    # the two bands are walked in opposite directions by the warm-started tracking, so the roots
+    # differ by rounding; next to caustics that rounding is amplified (flagged pixels)
+    clean = (top["flags"] == 0) & (bot["flags"][::-1] == 0)
+    assert clean.mean() > 0.99
     for k in ("A0", "A2", "A4"):
-        assert np.allclose(top[k], bot[k][::-1], rtol=1e-11, atol=0), k
+        rel = np.abs(top[k] / bot[k][::-1] - 1)
+        assert rel[clean].max() < 1e-9, (k, rel[clean].max())
+        assert np.median(rel) < 1e-14, k
     assert set(np.unique(top["nimg"])) <= {3, 5}
     assert top["A0"].min() >= 1.0
     assert ((top["flags"] & 3) == 0).all()

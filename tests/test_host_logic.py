@@ -99,8 +99,15 @@ def test_shard_ranges():
             assert max(sizes) - min(sizes) <= 1
     p = plan_map(8192, 3, 8, nchunks=4)
     assert p.row0 == 3072 and p.nrows == 1024 and sum(c[1] for c in p.chunks) == 1024
-    p = plan_map(10, 2, 3, nchunks=4)
+    assert all(c[0] % 32 == 0 for c in p.chunks)          # chunks start on strip boundaries
+    p = plan_map(10, 2, 3, nchunks=4, align=1)
     assert (p.row0, p.nrows, p.max_rows) == (7, 3, 4)
+    # aligned shards: boundaries are multiples of the strip length, nothing lost, nothing doubled
+    for n in (100, 8192, 203):
+        parts = [shard_range(n, r, 3, align=32) for r in range(3)]
+        assert parts[0][0] == 0 and parts[-1][1] == n
+        assert all(parts[i][1] == parts[i + 1][0] for i in range(2))
+        assert all(a % 32 == 0 for a, _ in parts)
 
 
 def test_map_coordinates_are_pixel_centres():
