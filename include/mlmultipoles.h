@@ -61,7 +61,7 @@ int mlm_synchronize(mlm_context* ctx);
 int mlm_alloc_host(mlm_context* ctx, int64_t bytes, void** out);
 int mlm_free_host(mlm_context* ctx, void* p);
 
-/* rows per warm-start strip of mlm_map (default 32; env MLM_MAP_STRIP at mlm_create) */
+/* rows per warm-start strip of mlm_map (default 64; env MLM_MAP_STRIP at mlm_create) */
 int mlm_map_strip(mlm_context* ctx);
 
 /* ---- the fused path: replaces the per-position body of example(), multipoles.py:181-202

@@ -7,11 +7,10 @@
 //   (d) W_2..W_6 per image                        reference: multipoles.py:197-201
 //   (e) mu0, mu2, mu4 per image and the sums      reference: multipoles.py:91-146
 //
-// (e) is NOT a transcription of the reference's (xi, eta) recursion.  It works in the
-// Wirtinger basis (d/dzeta, d/dzetabar), scaled so that dzbar/dzetabar = 1, where
-//   * only 14 of the 20 Taylor coefficients up to order 5 are needed,
-//   * the order-5 contribution collapses to Re(R32) ("Wirtinger form"),
-//   * mu2 = mu0^4 * lap1, mu4 = 2 * mu0^6 * lap2.
+// (e) is NOT a transcription of the reference's (xi, eta) recursion over 20 Taylor factors a_kl:
+// mu2 and mu4 are the source-plane Laplacian and bi-Laplacian of mu0, evaluated in closed form with
+// image-plane derivative operators (see image_terms_from_W and DESIGN.md, "operator form"), ~140
+// FP64 instructions per image instead of ~1900 flop.
 // tests/ verifies it against the oracle's literal restatement of the reference formulae.
 //
 // The functions are __host__ __device__ so that tests/ can compile them with g++ into a
@@ -416,86 +415,71 @@ struct ImageTerms {
 };
 
 // ORDER = 2: mu0, mu2 (quadrupole, needs W2..W4);  ORDER = 4: also mu4 (needs W2..W6)
+//
+// Closed form ("operator form").  With w = W2 and the image-plane operators
+//   D = d/dz + w d/dzbar,  Dbar = wbar d/dz + d/dzbar   (so that d/dzeta = mu0 D, d/dzetabar = mu0 Dbar)
+// acting on functions of (w, W3, W4, ... and conjugates; D W_k = W_{k+1}, D conj(W_k) = w conj(W_{k+1})),
+// the source-plane Laplacian L = d/dzeta d/dzetabar of mu0 = 1/(1-|w|^2) is
+//   mu2 = L mu0     = mu0^4 (3 mu0 |A|^2 + B),              A = Dbar |w|^2,  B = D A (real)
+//   mu4 = 2 L^2 mu0 = 2 mu0^6 lap2,  lap2 = Re[6 mu0^2 conj(A) H + 5 mu0 conj(A) E + mu0 D H + D E]
+// with C = Dbar A, E = Dbar B, H = 15 mu0 |A|^2 A + 7 A B + 3 conj(A) C.  These are the same numbers as
+// the reference's mu2, mu4 (multipoles.py:142-143), which it reaches through the 20 Taylor factors
+// a_kl; tests/ checks this function against the oracle's literal restatement of that recursion.
 template <int ORDER>
 MLM_HD ImageTerms image_terms_from_W(cd W2, cd W3, cd W4, cd W5, cd W6) {
-    // F_j = conj(W_{j+1}) are the derivatives of conj(W1) with respect to zbar.
-    const cd w = W2;
-    const cd F2 = conj(W3), F3 = conj(W4);
-    const double w2n = norm2(w);
-    const double mu0 = rcp(1.0 - w2n);               // signed, multipoles.py:91
-    const cd ww = csq(w);
-    const cd www = cmul(ww, w);
-
-    // order 2:  R20 = F2 w^2, R11 = F2 w, R02 = F2;   u_mn = mu0 (conj(R_nm) + w R_mn)
-    const cd R20 = cmul(F2, ww), R11 = cmul(F2, w), R02 = F2;
-    const cd u20 = scale(mu0, cfma(w, R20, conj(R02)));
-    const cd u11 = scale(mu0, cfma(w, R11, conj(R11)));
-    const cd u02 = scale(mu0, cfma(w, R02, conj(R20)));
-
-    // order 3
-    const cd t1 = cmul(u20, w), t2 = cmul(u11, w), t3 = cmul(u02, w);
-    const cd R30 = cfma(F3, www, cmul(F2, scale(3.0, t1)));
-    const cd R21 = cfma(F3, ww, cmul(F2, rfma(2.0, t2, u20)));
-    const cd R12 = cfma(F3, w, cmul(F2, rfma(2.0, u11, t3)));
-    const cd R03 = F3 + cmul(F2, scale(3.0, u02));
-    const cd u30 = scale(mu0, cfma(w, R30, conj(R03)));
-    const cd u21 = scale(mu0, cfma(w, R21, conj(R12)));
-    const cd u12 = scale(mu0, cfma(w, R12, conj(R21)));
-    const cd u03 = scale(mu0, cfma(w, R03, conj(R30)));
-
-    ImageTerms out;
-    out.mu0 = mu0;
+    const cd w = W2, w1 = W3, w2 = W4;
+    const double n = norm2(w);
+    const double mu0 = rcp(1.0 - n);                 // signed, multipoles.py:91
+    const double p = norm2(w1);
+    const cd wb = conj(w);
+    const cd wb2 = csq(wb);
+    const cd ww1b = cmul(w, conj(w1));
+    const cd A = cfma(wb2, w1, ww1b);                 // wbar^2 w1 + w conj(w1)
+    const double B = fma(2.0, re_mul(wb2, w2), p * fma(2.0, n, 1.0));
+    const double a2 = norm2(A);
     const double mu02 = mu0 * mu0;
     const double mu04 = mu02 * mu02;
-    // lap1 = 2 Re(R21) + |u02|^2 - |u20|^2
-    const double lap1 = fma(2.0, R21.x, norm2(u02) - norm2(u20));
-    out.mu2 = mu04 * lap1;
+    ImageTerms out;
+    out.mu0 = mu0;
+    out.mu2 = mu04 * fma(3.0 * mu0, a2, B);
     out.mu4 = 0.0;
     if (ORDER >= 4) {
-        const cd F4 = conj(W5), F5 = conj(W6);
-        // shared products
-        const cd p_u21w = cmul(u21, w);
-        const cd p_u12w = cmul(u12, w);
-        const cd p_u11u20 = cmul(u11, u20);
-        const cd p_u11u02 = cmul(u11, u02);
-        const cd p_u11sq = csq(u11);
-        const cd p_u02u20 = cmul(u02, u20);
-        const cd t2w = cmul(t2, w);                   // u11 w^2
-        const cd t3w = cmul(t3, w);                   // u02 w^2
-        // order 4 (only 31, 22, 13 are needed)
-        // R31 = F2 (3 u21 w + 3 u11 u20 + u30) + 3 F3 (u11 w^2 + u20 w) + F4 w^3
-        cd R31 = cmul(F2, rfma(3.0, p_u21w + p_u11u20, u30));
-        R31 = cfma(F3, scale(3.0, t2w + t1), R31);
-        R31 = cfma(F4, www, R31);
-        // R22 = F2 (2 u12 w + 2 u11^2 + u02 u20 + 2 u21) + F3 (u02 w^2 + 4 u11 w + u20) + F4 w^2
-        cd R22 = cmul(F2, rfma(2.0, p_u12w + p_u11sq + u21, p_u02u20));
-        R22 = cfma(F3, rfma(4.0, t2, t3w + u20), R22);
-        R22 = cfma(F4, ww, R22);
-        // R13 = F2 (3 u12 + 3 u11 u02 + w u03) + 3 F3 (u11 + w u02) + F4 w
-        cd R13 = cmul(F2, rfma(3.0, u12 + p_u11u02, cmul(w, u03)));
-        R13 = cfma(F3, scale(3.0, u11 + t3), R13);
-        R13 = cfma(F4, w, R13);
-        const cd u31 = scale(mu0, cfma(w, R31, conj(R13)));
-        const cd u22 = scale(mu0, cfma(w, R22, conj(R22)));
-        const cd u13 = scale(mu0, cfma(w, R13, conj(R31)));
-        // order 5: only Re(R32) survives in lap2
-        // S2 = 3 u22 w + 6 u11 u21 + 3 u12 u20 + u02 u30 + 2 u31
-        cd S2 = cfma(u02, u30, scale(2.0, u31));
-        S2 = rfma(3.0, cfma(u22, w, cmul(u12, u20)), S2);
-        S2 = rfma(6.0, cmul(u11, u21), S2);
-        // S3 = w (3 u12 w + 6 u11^2 + 3 u02 u20 + 6 u21) + 6 u11 u20 + u30
-        cd in3 = rfma(3.0, p_u12w + p_u02u20, scale(6.0, p_u11sq + u21));
-        cd S3 = cfma(w, in3, rfma(6.0, p_u11u20, u30));
-        // S4 = w^2 (u02 w + 6 u11) + 3 u20 w
-        cd S4 = cfma(ww, rfma(6.0, u11, t3), scale(3.0, t1));
-        // Re(R32) = Re(F2 S2 + F3 S3 + F4 S4 + F5 w^3)
-        const double reR32 = re_mul(F2, S2) + re_mul(F3, S3) + re_mul(F4, S4) + re_mul(F5, www);
-        // lap2 = 2 Re R32 + 4 Re(u02 conj u13) - 4 Re(u20 conj u31)
-        //        + |u03|^2 - |u30|^2 + 3 |u12|^2 - 3 |u21|^2
-        double lap2 = 2.0 * reR32;
-        lap2 = fma(4.0, re_mulc(u02, u13) - re_mulc(u20, u31), lap2);
-        lap2 += norm2(u03) - norm2(u30);
-        lap2 = fma(3.0, norm2(u12) - norm2(u21), lap2);
+        const cd w3 = W5, w4 = W6;
+        const cd wb3 = cmul(wb2, wb);
+        // C = Dbar A = 3 |w1|^2 wbar + wbar^3 w2 + w conj(w2)
+        cd C = cmul(w, conj(w2));
+        C = cfma(wb3, w2, C);
+        C = rfma(3.0 * p, wb, C);
+        const cd U = cmul(conj(w1), w2);
+        const cd X = cmul(wb, U);                     // wbar conj(w1) w2
+        const cd Y = cmul(w1, conj(w2));
+        cd Z = cmul(wb3, w3);                         // wbar^3 w3 + w^2 conj(w3)
+        Z = cfma(conj(wb2), conj(w3), Z);
+        // S = 12 E + 3 D C = (45+33n) X + (15+57n) Y + 24 p A + 9 p w conj(w1) + 15 Z
+        cd S = scale(15.0, Z);
+        S = rfma(fma(33.0, n, 45.0), X, S);
+        S = rfma(fma(57.0, n, 15.0), Y, S);
+        S = rfma(24.0 * p, A, S);
+        S = rfma(9.0 * p, ww1b, S);
+        // Re(D E)
+        const double T = re_mul(wb, cmul(conj(w1), w3));          // Re(wbar conj(w1) w3)
+        const cd Dp = cfma(w, Y, U);                              // D |w1|^2
+        const cd XY = rfma(2.0, Y, X);                            // X + 2 Y
+        double reDE = 2.0 * re_mulc(XY, A);                       // Re(conj(A) (2 X + 4 Y))
+        reDE = fma(fma(2.0, n, 3.0), re_mul(ww1b, U), reDE);
+        reDE = fma(fma(fma(2.0, n, 7.0), n, 1.0), norm2(w2), reDE);
+        reDE = fma(fma(9.0, n, 6.0), T, reDE);
+        reDE = fma(2.0, re_mul(A, Dp) + fma(p, B, re_mul(wb3, w4)), reDE);
+        // lap2 = mu0 { mu0 [ 105 mu0 a2^2 + 72 a2 B + 33 Re(conj(A)^2 C) ] + 7 B^2 + 3 |C|^2 + Re(conj(A) S) } + Re(D E)
+        const cd Ab2 = csq(conj(A));
+        double in1 = (105.0 * mu0) * (a2 * a2);
+        in1 = fma(72.0 * a2, B, in1);
+        in1 = fma(33.0, re_mul(Ab2, C), in1);
+        double in2 = re_mulc(S, A);
+        in2 = fma(3.0, norm2(C), in2);
+        in2 = fma(7.0 * B, B, in2);
+        in2 = fma(mu0, in1, in2);
+        const double lap2 = fma(mu0, in2, reDE);
         out.mu4 = 2.0 * (mu04 * mu02) * lap2;
     }
     return out;

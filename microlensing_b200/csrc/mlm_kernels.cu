@@ -26,7 +26,7 @@ using namespace mlm;
 
 #define MLM_BLOCK 128
 #ifndef MLM_MAP_MINBLOCKS
-#define MLM_MAP_MINBLOCKS 3          /* k_map: <= 168 registers -> 3 blocks (12 warps) per SM, no spill */
+#define MLM_MAP_MINBLOCKS 4          /* k_map: <= 128 registers -> 4 blocks (16 warps) per SM, no spill */
 #endif
 
 // ------------------------------------------------------------------------------------------
@@ -235,7 +235,7 @@ struct mlm_context {
     std::atomic<int64_t> launches{0};
     std::string err;
     int sm_count = 148;
-    int map_strip = 32;                                // rows per warm-start strip of k_map (MLM_MAP_STRIP)
+    int map_strip = 64;                                // rows per warm-start strip of k_map (MLM_MAP_STRIP)
 };
 
 static std::string g_err;

@@ -18,7 +18,7 @@ __all__ = ["shard_range", "ShardPlan", "plan_map", "BYTES_PER_POSITION", "Sharde
 BYTES_PER_POSITION = 26           # 3 x float64 + 2 x uint8
 
 
-MAP_STRIP = 32                    # default rows per warm-start strip of the map kernel (mlm_map_strip)
+MAP_STRIP = 64                    # default rows per warm-start strip of the map kernel (mlm_map_strip)
 
 
 def shard_range(n: int, rank: int, world: int, align: int = 1) -> tuple[int, int]:

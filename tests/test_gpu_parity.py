@@ -236,7 +236,7 @@ def test_row_sharding_is_bitwise_identical(mb):
     x0, y0, dx, dy = -0.88, -0.8, 1.6 / nx, 1.6 / ny
     full = mb.magnification_map(s, q, rho, G, x0, y0, dx, dy, nx, ny)
     strip = mb._capi.context().lib.mlm_map_strip(mb._capi.context().handle)
-    assert strip == 32
+    assert strip == 64
     for world in (2, 3, 8):
         parts = []
         for r in range(world):

@@ -99,7 +99,7 @@ def test_shard_ranges():
             assert max(sizes) - min(sizes) <= 1
     p = plan_map(8192, 3, 8, nchunks=4)
     assert p.row0 == 3072 and p.nrows == 1024 and sum(c[1] for c in p.chunks) == 1024
-    assert all(c[0] % 32 == 0 for c in p.chunks)          # chunks start on strip boundaries
+    assert all(c[0] % 64 == 0 for c in p.chunks)          # chunks start on strip boundaries
     p = plan_map(10, 2, 3, nchunks=4, align=1)
     assert (p.row0, p.nrows, p.max_rows) == (7, 3, 4)
     # aligned shards: boundaries are multiples of the strip length, nothing lost, nothing doubled
