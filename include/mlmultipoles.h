@@ -22,7 +22,8 @@
  *    zeta = zeta_cm - s q/(1+q) themselves (multipoles.py:177-178);
  *  - order = 2 computes A0, A2 (quadrupole, multipoles.py:12-65; A4 output is set to 0),
  *    order = 4 computes A0, A2, A4 (hexadecapole, multipoles.py:67-148);
- *  - nimg / flags outputs may be NULL.
+ *  - any of the per-position outputs A0 / A2 / A4 / nimg / flags may be NULL (not stored, not
+ *    copied back); at least one must be given.
  * There is no CPU fallback anywhere in the library: without a CUDA device mlm_create fails.
  */
 #ifndef MLMULTIPOLES_H
@@ -60,6 +61,18 @@ int mlm_synchronize(mlm_context* ctx);
 /* pinned host memory for *_host outputs (so the D2H copies overlap with the kernels) */
 int mlm_alloc_host(mlm_context* ctx, int64_t bytes, void** out);
 int mlm_free_host(mlm_context* ctx, void* p);
+
+/* Device buffers that the other processes of the box can map into their address space
+ * (cudaMalloc + CUDA IPC).  Multi-GPU maps use them for the final gather: rank 0
+ * allocates the full-map outputs and exports the handle, every other rank opens it and passes
+ * pointers INTO IT to mlm_map, whose kernel then stores its rows straight into rank 0's HBM over
+ * NVLink (peer stores from the kernel epilogue; no separate collective, no staging copy). */
+#define MLM_IPC_HANDLE_BYTES 64
+int mlm_device_alloc(mlm_context* ctx, int64_t bytes, void** out);
+int mlm_device_free(mlm_context* ctx, void* p);
+int mlm_ipc_export(mlm_context* ctx, void* p, unsigned char* handle /* [MLM_IPC_HANDLE_BYTES] */);
+int mlm_ipc_open(mlm_context* ctx, const unsigned char* handle, void** out);
+int mlm_ipc_close(mlm_context* ctx, void* p);
 
 /* rows per warm-start strip of mlm_map (default 64; env MLM_MAP_STRIP at mlm_create) */
 int mlm_map_strip(mlm_context* ctx);

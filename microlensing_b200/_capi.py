@@ -28,6 +28,11 @@ SIGNATURES = {
     "mlm_map_strip": [_P],
     "mlm_alloc_host": [_P, _L, ctypes.POINTER(_P)],
     "mlm_free_host": [_P, _P],
+    "mlm_device_alloc": [_P, _L, ctypes.POINTER(_P)],
+    "mlm_device_free": [_P, _P],
+    "mlm_ipc_export": [_P, _P, ctypes.c_char_p],
+    "mlm_ipc_open": [_P, ctypes.c_char_p, ctypes.POINTER(_P)],
+    "mlm_ipc_close": [_P, _P],
     "mlm_points": [_P, _D, _D, _D, _D, _P, _L, _I, _P, _P, _P, _P, _P, _P],
     "mlm_points_host": [_P, _D, _D, _D, _D, _P, _L, _I, _P, _P, _P, _P, _P],
     "mlm_map": [_P, _D, _D, _D, _D, _D, _D, _D, _D, _L, _L, _L, _I, _P, _P, _P, _P, _P, _P],
@@ -116,6 +121,28 @@ class Context:
         a = (ctypes.c_int32 * 4)()
         self.check(self.lib.mlm_kernel_info(self.handle, a, 4), "mlm_kernel_info")
         return {"k_points4_regs": a[0], "k_points4_local_bytes": a[1], "k_map4_regs": a[2], "k_map4_local_bytes": a[3]}
+
+    # ---- device buffers shareable across the processes of one box (CUDA IPC) -----------------
+    def device_alloc(self, nbytes: int) -> int:
+        p = _P()
+        self.check(self.lib.mlm_device_alloc(self.handle, int(nbytes), ctypes.byref(p)), "mlm_device_alloc")
+        return int(p.value)
+
+    def device_free(self, p: int):
+        self.check(self.lib.mlm_device_free(self.handle, _P(p)), "mlm_device_free")
+
+    def ipc_export(self, p: int) -> bytes:
+        buf = ctypes.create_string_buffer(64)
+        self.check(self.lib.mlm_ipc_export(self.handle, _P(p), buf), "mlm_ipc_export")
+        return buf.raw
+
+    def ipc_open(self, handle: bytes) -> int:
+        p = _P()
+        self.check(self.lib.mlm_ipc_open(self.handle, ctypes.c_char_p(handle), ctypes.byref(p)), "mlm_ipc_open")
+        return int(p.value)
+
+    def ipc_close(self, p: int):
+        self.check(self.lib.mlm_ipc_close(self.handle, _P(p)), "mlm_ipc_close")
 
     def pinned_empty(self, shape, dtype) -> np.ndarray:
         """numpy array over page-locked host memory (freed when the array and its views die)."""

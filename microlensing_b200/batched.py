@@ -13,7 +13,7 @@ import numpy as np
 from . import _capi
 
 __all__ = ["Magnification", "magnification_points", "magnification_map", "magnification_models",
-           "map_coordinates", "lightcurve_coordinates", "alloc_outputs", "map_device", "points_device",
+           "map_coordinates", "lightcurve_coordinates", "alloc_outputs", "ALL_OUTPUTS", "map_device", "points_device",
            "models_device"]
 
 
@@ -22,19 +22,35 @@ class Magnification(dict):
     __getattr__ = dict.__getitem__
 
 
-def alloc_outputs(shape, device=None, pinned=True) -> Magnification:
-    """Output buffers (page-locked by default so D2H overlaps with compute)."""
+_OUT_DTYPES = (("A0", np.float64), ("A2", np.float64), ("A4", np.float64), ("nimg", np.uint8), ("flags", np.uint8))
+ALL_OUTPUTS = tuple(k for k, _ in _OUT_DTYPES)
+
+
+def alloc_outputs(shape, device=None, pinned=True, outputs=ALL_OUTPUTS) -> Magnification:
+    """Output buffers (page-locked by default so D2H overlaps with compute).  `outputs` selects
+    which of A0, A2, A4, nimg, flags are wanted; the others are neither stored by the kernel nor
+    copied back (the C ABI takes NULL for them)."""
+    bad = set(outputs) - set(ALL_OUTPUTS)
+    if bad or not outputs:
+        raise ValueError(f"outputs must be a non-empty subset of {ALL_OUTPUTS}")
     ctx = _capi.context(device)
     mk = (lambda dt: ctx.pinned_empty(shape, dt)) if pinned else (lambda dt: np.empty(shape, dt))
-    return Magnification(A0=mk(np.float64), A2=mk(np.float64), A4=mk(np.float64),
-                         nimg=mk(np.uint8), flags=mk(np.uint8))
+    return Magnification({k: mk(dt) for k, dt in _OUT_DTYPES if k in outputs})
 
 
 def _check_out(out, shape):
-    for k, dt in (("A0", np.float64), ("A2", np.float64), ("A4", np.float64), ("nimg", np.uint8), ("flags", np.uint8)):
-        a = out[k]
+    if not any(k in out for k in ALL_OUTPUTS):
+        raise ValueError(f"out must hold at least one of {ALL_OUTPUTS}")
+    for k, dt in _OUT_DTYPES:
+        a = out.get(k)
+        if a is None:
+            continue
         if a.shape != tuple(shape) or a.dtype != dt or not a.flags.c_contiguous:
             raise ValueError(f"out[{k!r}] must be C-contiguous {dt} of shape {tuple(shape)}")
+
+
+def _out_ptrs(out):
+    return [_capi.ptr(out.get(k)) for k in ALL_OUTPUTS]
 
 
 def map_coordinates(s, q, x0, y0, dx, dy, nx, ny, row0=0, nrows=None):
@@ -60,7 +76,8 @@ def lightcurve_coordinates(s, q, u0, alpha, tau0, dtau, T):
     return zx + 1j * zy
 
 
-def magnification_points(s, q, rho, Gamma, zeta, order=4, out=None, device=None) -> Magnification:
+def magnification_points(s, q, rho, Gamma, zeta, order=4, out=None, device=None,
+                         outputs=ALL_OUTPUTS) -> Magnification:
     """A0/A2/A4, image count and flags at arbitrary primary-frame positions `zeta` (any shape).
 
     Per position this is the body of example(), multipoles.py:181-202.
@@ -69,31 +86,30 @@ def magnification_points(s, q, rho, Gamma, zeta, order=4, out=None, device=None)
     shape = np.shape(zeta)
     zeta = np.ascontiguousarray(zeta, dtype=np.complex128).reshape(shape)   # ascontiguousarray makes 0-d into 1-d
     if out is None:
-        out = alloc_outputs(shape, device, pinned=zeta.size >= (1 << 16))
+        out = alloc_outputs(shape, device, pinned=zeta.size >= (1 << 16), outputs=outputs)
     _check_out(out, shape)
     ctx.check(ctx.lib.mlm_points_host(ctx.handle, s, q, rho, Gamma, _capi.ptr(zeta), zeta.size, order,
-                                      _capi.ptr(out["A0"]), _capi.ptr(out["A2"]), _capi.ptr(out["A4"]),
-                                      _capi.ptr(out["nimg"]), _capi.ptr(out["flags"])), "mlm_points_host")
+                                      *_out_ptrs(out)), "mlm_points_host")
     return out
 
 
 def magnification_map(s, q, rho, Gamma, x0, y0, dx, dy, nx, ny, row0=0, nrows=None, order=4, out=None,
-                      device=None) -> Magnification:
+                      device=None, outputs=ALL_OUTPUTS) -> Magnification:
     """Rows [row0, row0+nrows) of an nx x ny magnification map (centre-of-mass window, pixel-centre
     sampling); coordinates are generated on the GPU, results land in `out` (nrows, nx)."""
     ctx = _capi.context(device)
     nrows = ny - row0 if nrows is None else nrows
     shape = (nrows, nx)
     if out is None:
-        out = alloc_outputs(shape, device, pinned=nrows * nx >= (1 << 16))
+        out = alloc_outputs(shape, device, pinned=nrows * nx >= (1 << 16), outputs=outputs)
     _check_out(out, shape)
     ctx.check(ctx.lib.mlm_map_host(ctx.handle, s, q, rho, Gamma, x0, y0, dx, dy, nx, row0, nrows, order,
-                                   _capi.ptr(out["A0"]), _capi.ptr(out["A2"]), _capi.ptr(out["A4"]),
-                                   _capi.ptr(out["nimg"]), _capi.ptr(out["flags"])), "mlm_map_host")
+                                   *_out_ptrs(out)), "mlm_map_host")
     return out
 
 
-def magnification_models(s, q, rho, Gamma, u0, alpha, tau0, dtau, T, order=4, out=None, device=None) -> Magnification:
+def magnification_models(s, q, rho, Gamma, u0, alpha, tau0, dtau, T, order=4, out=None, device=None,
+                         outputs=ALL_OUTPUTS) -> Magnification:
     """Batched fit grid: M models (arrays s, q, rho, Gamma, u0, alpha of length M) x T epochs."""
     ctx = _capi.context(device)
     arrs = [np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float64), np.shape(s)))
@@ -103,11 +119,10 @@ def magnification_models(s, q, rho, Gamma, u0, alpha, tau0, dtau, T, order=4, ou
         raise ValueError("magnification_models: s and q must be positive")
     shape = (M, T)
     if out is None:
-        out = alloc_outputs(shape, device, pinned=M * T >= (1 << 16))
+        out = alloc_outputs(shape, device, pinned=M * T >= (1 << 16), outputs=outputs)
     _check_out(out, shape)
     ctx.check(ctx.lib.mlm_models_host(ctx.handle, *[_capi.ptr(a) for a in arrs], M, tau0, dtau, T, order,
-                                      _capi.ptr(out["A0"]), _capi.ptr(out["A2"]), _capi.ptr(out["A4"]),
-                                      _capi.ptr(out["nimg"]), _capi.ptr(out["flags"])), "mlm_models_host")
+                                      *_out_ptrs(out)), "mlm_models_host")
     return out
 
 

@@ -35,9 +35,9 @@ using namespace mlm;
 __device__ __forceinline__ void store_result(const PointResult& r, int64_t i, double* __restrict__ A0,
                                              double* __restrict__ A2, double* __restrict__ A4,
                                              uint8_t* __restrict__ nimg, uint8_t* __restrict__ flags) {
-    A0[i] = r.A0;
-    A2[i] = r.A2;
-    A4[i] = r.A4;
+    if (A0) A0[i] = r.A0;
+    if (A2) A2[i] = r.A2;
+    if (A4) A4[i] = r.A4;
     if (nimg) nimg[i] = (uint8_t)r.nimg;
     if (flags) flags[i] = (uint8_t)r.flags;
 }
@@ -374,13 +374,58 @@ int mlm_free_host(mlm_context* ctx, void* p) {
     return 0;
 }
 
+// ---- device buffers that other processes of the box can map (multi-GPU gather without a copy) ----
+int mlm_device_alloc(mlm_context* ctx, int64_t bytes, void** out) {
+    if (!ctx || !out || bytes <= 0) return fail(ctx, MLM_EINVAL, "mlm_device_alloc: bad argument");
+    DeviceGuard g(ctx->device);
+    *out = nullptr;
+    CK(cudaMalloc(out, (size_t)bytes));                // plain cudaMalloc: exportable with cudaIpcGetMemHandle
+    return 0;
+}
+
+int mlm_device_free(mlm_context* ctx, void* p) {
+    if (!ctx) return fail(ctx, MLM_EINVAL, "mlm_device_free: NULL context");
+    if (!p) return 0;
+    DeviceGuard g(ctx->device);
+    CK(cudaFree(p));
+    return 0;
+}
+
+int mlm_ipc_export(mlm_context* ctx, void* p, unsigned char* handle) {
+    if (!ctx || !p || !handle) return fail(ctx, MLM_EINVAL, "mlm_ipc_export: NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == MLM_IPC_HANDLE_BYTES, "handle size");
+    DeviceGuard g(ctx->device);
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, p));
+    memcpy(handle, &h, sizeof(h));
+    return 0;
+}
+
+int mlm_ipc_open(mlm_context* ctx, const unsigned char* handle, void** out) {
+    if (!ctx || !handle || !out) return fail(ctx, MLM_EINVAL, "mlm_ipc_open: NULL argument");
+    DeviceGuard g(ctx->device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    *out = nullptr;
+    CK(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+
+int mlm_ipc_close(mlm_context* ctx, void* p) {
+    if (!ctx) return fail(ctx, MLM_EINVAL, "mlm_ipc_close: NULL context");
+    if (!p) return 0;
+    DeviceGuard g(ctx->device);
+    CK(cudaIpcCloseMemHandle(p));
+    return 0;
+}
+
 // ---- fused path, device pointers --------------------------------------------------------------
 int mlm_points(mlm_context* ctx, double s, double q, double rho, double Gamma, const double* zeta, int64_t n,
                int order, double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags, void* stream) {
     if (!ctx) return fail(ctx, MLM_EINVAL, "mlm_points: NULL context");
     if (n < 0 || (order != 2 && order != 4) || bad_lens(s, q)) return fail(ctx, MLM_EINVAL, "mlm_points: bad argument");
     if (n == 0) return 0;
-    if (!zeta || !A0 || !A2 || !A4) return fail(ctx, MLM_EINVAL, "mlm_points: NULL buffer");
+    if (!zeta || !(A0 || A2 || A4 || nimg || flags)) return fail(ctx, MLM_EINVAL, "mlm_points: NULL buffer");
     DeviceGuard g(ctx->device);
     LensTable T;
     make_table(s, q, &T);
@@ -403,7 +448,7 @@ int mlm_map(mlm_context* ctx, double s, double q, double rho, double Gamma, doub
     if (nx < 0 || nrows < 0 || (order != 2 && order != 4) || bad_lens(s, q))
         return fail(ctx, MLM_EINVAL, "mlm_map: bad argument");
     if (nx == 0 || nrows == 0) return 0;
-    if (!A0 || !A2 || !A4) return fail(ctx, MLM_EINVAL, "mlm_map: NULL buffer");
+    if (!(A0 || A2 || A4 || nimg || flags)) return fail(ctx, MLM_EINVAL, "mlm_map: NULL buffer");
     DeviceGuard g(ctx->device);
     LensTable T;
     make_table(s, q, &T);
@@ -428,7 +473,7 @@ int mlm_models(mlm_context* ctx, const double* s, const double* q, const double*
     if (!ctx) return fail(ctx, MLM_EINVAL, "mlm_models: NULL context");
     if (M < 0 || Tn < 0 || (order != 2 && order != 4)) return fail(ctx, MLM_EINVAL, "mlm_models: bad argument");
     if (M == 0 || Tn == 0) return 0;
-    if (!s || !q || !rho || !Gamma || !u0 || !alpha || !A0 || !A2 || !A4)
+    if (!s || !q || !rho || !Gamma || !u0 || !alpha || !(A0 || A2 || A4 || nimg || flags))
         return fail(ctx, MLM_EINVAL, "mlm_models: NULL buffer");
     DeviceGuard g(ctx->device);
     int64_t bx = (Tn + MLM_BLOCK - 1) / MLM_BLOCK;
@@ -530,9 +575,9 @@ static int carve(mlm_context* ctx, int64_t n, bool with_zeta, Scratch* sc) {
 // copy one chunk of results back on `st`
 static int d2h_chunk(mlm_context* ctx, const Scratch& sc, int64_t off, int64_t cnt, double* A0, double* A2,
                      double* A4, uint8_t* nimg, uint8_t* flags, cudaStream_t st) {
-    CK(cudaMemcpyAsync(A0 + off, sc.A0 + off, cnt * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(A2 + off, sc.A2 + off, cnt * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(A4 + off, sc.A4 + off, cnt * 8, cudaMemcpyDeviceToHost, st));
+    if (A0) CK(cudaMemcpyAsync(A0 + off, sc.A0 + off, cnt * 8, cudaMemcpyDeviceToHost, st));
+    if (A2) CK(cudaMemcpyAsync(A2 + off, sc.A2 + off, cnt * 8, cudaMemcpyDeviceToHost, st));
+    if (A4) CK(cudaMemcpyAsync(A4 + off, sc.A4 + off, cnt * 8, cudaMemcpyDeviceToHost, st));
     if (nimg) CK(cudaMemcpyAsync(nimg + off, sc.nimg + off, cnt, cudaMemcpyDeviceToHost, st));
     if (flags) CK(cudaMemcpyAsync(flags + off, sc.flags + off, cnt, cudaMemcpyDeviceToHost, st));
     return 0;
@@ -546,7 +591,7 @@ int mlm_points_host(mlm_context* ctx, double s, double q, double rho, double Gam
     if (n < 0 || (order != 2 && order != 4) || bad_lens(s, q))
         return fail(ctx, MLM_EINVAL, "mlm_points_host: bad argument");
     if (n == 0) return 0;
-    if (!zeta || !A0 || !A2 || !A4) return fail(ctx, MLM_EINVAL, "mlm_points_host: NULL buffer");
+    if (!zeta || !(A0 || A2 || A4 || nimg || flags)) return fail(ctx, MLM_EINVAL, "mlm_points_host: NULL buffer");
     DeviceGuard g(ctx->device);
     Scratch sc;
     int rc = carve(ctx, n, true, &sc);
@@ -557,8 +602,9 @@ int mlm_points_host(mlm_context* ctx, double s, double q, double rho, double Gam
         const int64_t cnt = (n - off < MLM_CHUNK_POINTS) ? (n - off) : MLM_CHUNK_POINTS;
         cudaStream_t st = ctx->stream[k & 1];
         CK(cudaMemcpyAsync(sc.zeta + 2 * off, zeta + 2 * off, cnt * 16, cudaMemcpyHostToDevice, st));
-        rc = mlm_points(ctx, s, q, rho, Gamma, sc.zeta + 2 * off, cnt, order, sc.A0 + off, sc.A2 + off, sc.A4 + off,
-                        sc.nimg + off, sc.flags + off, st);
+        rc = mlm_points(ctx, s, q, rho, Gamma, sc.zeta + 2 * off, cnt, order, A0 ? sc.A0 + off : nullptr,
+                        A2 ? sc.A2 + off : nullptr, A4 ? sc.A4 + off : nullptr, nimg ? sc.nimg + off : nullptr,
+                        flags ? sc.flags + off : nullptr, st);
         if (rc) return rc;
         rc = d2h_chunk(ctx, sc, off, cnt, A0, A2, A4, nimg, flags, st);
         if (rc) return rc;
@@ -575,7 +621,7 @@ int mlm_map_host(mlm_context* ctx, double s, double q, double rho, double Gamma,
     if (nx < 0 || nrows < 0 || (order != 2 && order != 4) || bad_lens(s, q))
         return fail(ctx, MLM_EINVAL, "mlm_map_host: bad argument");
     if (nx == 0 || nrows == 0) return 0;
-    if (!A0 || !A2 || !A4) return fail(ctx, MLM_EINVAL, "mlm_map_host: NULL buffer");
+    if (!(A0 || A2 || A4 || nimg || flags)) return fail(ctx, MLM_EINVAL, "mlm_map_host: NULL buffer");
     DeviceGuard g(ctx->device);
     const int64_t n = nx * nrows;
     Scratch sc;
@@ -588,8 +634,9 @@ int mlm_map_host(mlm_context* ctx, double s, double q, double rho, double Gamma,
         const int64_t nr = (nrows - r < rows_per) ? (nrows - r) : rows_per;
         const int64_t off = r * nx, cnt = nr * nx;
         cudaStream_t st = ctx->stream[k & 1];
-        rc = mlm_map(ctx, s, q, rho, Gamma, x0, y0, dx, dy, nx, row0 + r, nr, order, sc.A0 + off, sc.A2 + off,
-                     sc.A4 + off, sc.nimg + off, sc.flags + off, st);
+        rc = mlm_map(ctx, s, q, rho, Gamma, x0, y0, dx, dy, nx, row0 + r, nr, order, A0 ? sc.A0 + off : nullptr,
+                     A2 ? sc.A2 + off : nullptr, A4 ? sc.A4 + off : nullptr, nimg ? sc.nimg + off : nullptr,
+                     flags ? sc.flags + off : nullptr, st);
         if (rc) return rc;
         rc = d2h_chunk(ctx, sc, off, cnt, A0, A2, A4, nimg, flags, st);
         if (rc) return rc;
@@ -605,7 +652,7 @@ int mlm_models_host(mlm_context* ctx, const double* s, const double* q, const do
     if (!ctx) return fail(ctx, MLM_EINVAL, "mlm_models_host: NULL context");
     if (M < 0 || Tn < 0 || (order != 2 && order != 4)) return fail(ctx, MLM_EINVAL, "mlm_models_host: bad argument");
     if (M == 0 || Tn == 0) return 0;
-    if (!s || !q || !rho || !Gamma || !u0 || !alpha || !A0 || !A2 || !A4)
+    if (!s || !q || !rho || !Gamma || !u0 || !alpha || !(A0 || A2 || A4 || nimg || flags))
         return fail(ctx, MLM_EINVAL, "mlm_models_host: NULL buffer");
     DeviceGuard g(ctx->device);
     const int64_t n = M * Tn;
@@ -630,8 +677,9 @@ int mlm_models_host(mlm_context* ctx, const double* s, const double* q, const do
         const int64_t off = m0 * Tn, cnt = nm * Tn;
         cudaStream_t st = ctx->stream[k & 1];
         rc = mlm_models(ctx, par + m0, par + mpad + m0, par + 2 * mpad + m0, par + 3 * mpad + m0, par + 4 * mpad + m0,
-                        par + 5 * mpad + m0, nm, tau0, dtau, Tn, order, sc.A0 + off, sc.A2 + off, sc.A4 + off,
-                        sc.nimg + off, sc.flags + off, st);
+                        par + 5 * mpad + m0, nm, tau0, dtau, Tn, order, A0 ? sc.A0 + off : nullptr,
+                        A2 ? sc.A2 + off : nullptr, A4 ? sc.A4 + off : nullptr, nimg ? sc.nimg + off : nullptr,
+                        flags ? sc.flags + off : nullptr, st);
         if (rc) return rc;
         rc = d2h_chunk(ctx, sc, off, cnt, A0, A2, A4, nimg, flags, st);
         if (rc) return rc;

@@ -3,8 +3,15 @@
 Every source position is independent (reference multipoles.py:184), so there is no exchange
 step on the data path: maps shard by contiguous row blocks, model grids by contiguous model
 ranges.  The only collective is the final gather of the SoA outputs to rank 0
-(26 B/position: A0, A2, A4 float64 + nimg, flags uint8) over NCCL / NVLink, issued per row
-chunk on a side stream so that it overlaps the kernel of the next chunk.
+(26 B/position: A0, A2, A4 float64 + nimg, flags uint8) over NVLink.  Two implementations:
+
+* gather="p2p" (default on CUDA, world > 1): rank 0 owns the full-map output buffers and shares
+  them with the other processes (CUDA IPC, mlm_ipc_*); every rank passes pointers into that buffer
+  to the map kernel, whose epilogue stores go straight into rank 0's HBM over NVLink while the
+  kernel is still computing -- the gather is fused into the kernel, one launch per rank, and a
+  1-element NCCL all-reduce on the compute stream is the completion fence.
+* gather="nccl": each rank computes into a local buffer chunk by chunk and torch.distributed
+  gathers every chunk to rank 0 on a side stream, overlapping the next chunk's kernel (baseline).
 
 torch / torch.distributed are plumbing here (device buffers, streams, NCCL); the arithmetic is
 in libmlmultipoles.so.
@@ -13,9 +20,10 @@ from __future__ import annotations
 
 from dataclasses import dataclass
 
-__all__ = ["shard_range", "ShardPlan", "plan_map", "BYTES_PER_POSITION", "ShardedMap"]
+__all__ = ["shard_range", "ShardPlan", "plan_map", "full_map_layout", "BYTES_PER_POSITION", "KEYS", "ShardedMap"]
 
 BYTES_PER_POSITION = 26           # 3 x float64 + 2 x uint8
+KEYS = (("A0", 8), ("A2", 8), ("A4", 8), ("nimg", 1), ("flags", 1))     # output arrays and their item sizes
 
 
 MAP_STRIP = 64                    # default rows per warm-start strip of the map kernel (mlm_map_strip)
@@ -60,49 +68,136 @@ def plan_map(ny: int, rank: int, world: int, nchunks: int = 4, align: int = MAP_
     return ShardPlan(rank, world, lo, n, max_rows, tuple(chunks))
 
 
-class ShardedMap:
-    """Device-resident, row-sharded magnification map with a chunk-pipelined NCCL gather.
+def full_map_layout(nx: int, ny: int) -> tuple[dict, int]:
+    """Byte offsets of the five full-map SoA arrays inside rank 0's shared buffer (each 256-byte
+    aligned) and the total size: {"A0": off, ...}, nbytes."""
+    off, out = 0, {}
+    for key, item in KEYS:
+        out[key] = off
+        off += (nx * ny * item + 255) // 256 * 256
+    return out, off
 
-    Each rank owns a byte buffer laid out [A0 | A2 | A4 | nimg | flags] for `max_rows` rows
-    (padded so that every rank contributes the same size).  `compute()` enqueues the map
-    kernel chunk by chunk on the compute stream; with world > 1, after every chunk the chunk's
-    rows are gathered to rank 0 on a communication stream (torch.distributed.gather over NCCL),
-    overlapping the next chunk's kernel.
+
+class _DevMem:
+    """Raw device allocation seen through __cuda_array_interface__ (so torch can view it)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+class ShardedMap:
+    """Device-resident, row-sharded magnification map with the gather to rank 0 (module docstring).
+
+    `compute()` only enqueues work on the current stream of `device`; after a stream / device
+    synchronisation rank 0 holds the whole map (`full_views()` / `assemble_host()`).
+    `compute_fn` (default: the CUDA map kernel through the C ABI) and device="cpu" exist so that
+    the N > 1 host logic (plan, offsets, chunk loop, gather placement) is testable with gloo.
     """
 
-    def __init__(self, nx: int, ny: int, rank: int = 0, world: int = 1, device=None, nchunks: int = 4, group=None,
-                 align: int = MAP_STRIP):
+    def __init__(self, nx: int, ny: int, rank: int = 0, world: int = 1, device=None, nchunks: int | None = None,
+                 group=None, align: int = MAP_STRIP, gather: str | None = None, compute_fn=None):
         import torch
         self.torch = torch
         self.nx, self.ny = nx, ny
         self.align = align
-        self.plan = plan_map(ny, rank, world, nchunks, align)
         self.group = group
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.on_cuda = self.device.type == "cuda"
+        if gather is None:
+            gather = "none" if world == 1 else ("p2p" if self.on_cuda else "nccl")
+        if gather not in ("none", "p2p", "nccl"):
+            raise ValueError("gather must be 'none', 'p2p' or 'nccl'")
+        self.gather = gather
+        if nchunks is None:
+            nchunks = 4 if (world > 1 and gather == "nccl") else 1       # chunks only pipeline the NCCL gather
+        self.plan = plan_map(ny, rank, world, nchunks, align)
+        self.compute_fn = compute_fn
         n_slot = self.plan.max_rows * nx
         self.n_slot = n_slot
-        with torch.cuda.device(self.device):
+        self.full = None
+        self.comm_stream = None
+        self._ipc = None
+        if gather == "p2p" and world > 1:
+            self._setup_p2p()
+        else:
             self.local = self._alloc(n_slot)
-            self.comm_stream = torch.cuda.Stream() if world > 1 else None
-            self.full = None
+            if world > 1 and self.on_cuda:
+                with torch.cuda.device(self.device):
+                    self.comm_stream = torch.cuda.Stream()
             if world > 1 and rank == 0:
                 self.full = [self._alloc(n_slot) if r else self.local for r in range(world)]
 
+    # ---- buffers ---------------------------------------------------------------------------------
     def _alloc(self, n):
         t = self.torch
-        return {"A0": t.empty(n, dtype=t.float64, device=self.device),
-                "A2": t.empty(n, dtype=t.float64, device=self.device),
-                "A4": t.empty(n, dtype=t.float64, device=self.device),
-                "nimg": t.empty(n, dtype=t.uint8, device=self.device),
-                "flags": t.empty(n, dtype=t.uint8, device=self.device)}
+        return {key: t.empty(n, dtype=t.float64 if item == 8 else t.uint8, device=self.device) for key, item in KEYS}
+
+    def _setup_p2p(self):
+        """Rank 0 allocates the full-map buffer and shares it; `local` becomes this rank's row
+        window INSIDE rank 0's memory (peer-mapped on ranks > 0)."""
+        import torch.distributed as dist
+        from . import _capi
+        t, p = self.torch, self.plan
+        ctx = _capi.context(self.device.index)
+        layout, nbytes = full_map_layout(self.nx, self.ny)
+        box = [None]
+        if p.rank == 0:
+            base = ctx.device_alloc(nbytes)
+            box[0] = ctx.ipc_export(base)
+        dist.broadcast_object_list(box, src=0, group=self.group)
+        if p.rank != 0:
+            base = ctx.ipc_open(box[0])
+        self._ipc = (ctx, base, p.rank == 0)
+        n = self.nx * self.ny
+        lo = p.row0 * self.nx
+        # launch targets: raw addresses of this rank's row window inside rank 0's buffer (peer-mapped
+        # on ranks > 0, where torch never touches the memory)
+        self.local = {key: base + layout[key] + lo * item for key, item in KEYS}
+        self.full_map = None
+        if p.rank == 0:
+            raw = t.as_tensor(_DevMem(base, nbytes), device=self.device)
+            self.full_map = {key: raw[layout[key]: layout[key] + n * item].view(t.float64 if item == 8 else t.uint8)
+                             for key, item in KEYS}
+        self._fence = t.zeros(1, dtype=t.float32, device=self.device)
+
+    def close(self):
+        """Release the shared buffer (collective: every rank unmaps before rank 0 frees)."""
+        if self._ipc is None:
+            return
+        import torch.distributed as dist
+        ctx, base, owner = self._ipc
+        self._ipc = None
+        self.local = self.full_map = None
+        self.torch.cuda.synchronize(self.device)
+        if not owner:
+            ctx.ipc_close(base)
+        dist.barrier(group=self.group)
+        if owner:
+            ctx.device_free(base)
+
+    # ---- work --------------------------------------------------------------------------------------
+    def _launch(self, s, q, rho, Gamma, x0, y0, dx, dy, row0, nrows, views, order, stream):
+        if self.compute_fn is not None:
+            self.compute_fn(s, q, rho, Gamma, x0, y0, dx, dy, self.nx, row0, nrows, views, order)
+            return
+        from .batched import map_device
+        map_device(s, q, rho, Gamma, x0, y0, dx, dy, self.nx, row0, nrows, views["A0"], views["A2"], views["A4"],
+                   views["nimg"], views["flags"], order=order, stream=stream, device=self.device.index)
 
     def compute(self, s, q, rho, Gamma, x0, y0, dx, dy, order=4, gather=True):
         """Enqueue this rank's shard (and the gather to rank 0 when world > 1)."""
         import torch.distributed as dist
-        from .batched import map_device
         t = self.torch
         p, nx = self.plan, self.nx
-        cur = t.cuda.current_stream(self.device)
+        cur = t.cuda.current_stream(self.device) if self.on_cuda else None
+        stream = cur.cuda_stream if cur is not None else None
+        if self.gather == "p2p" and p.world > 1:
+            # one launch; the kernel's stores ARE the gather (peer memory on ranks > 0)
+            if p.nrows:
+                self._launch(s, q, rho, Gamma, x0, y0, dx, dy, p.row0, p.nrows, self.local, order, stream)
+            if gather:
+                dist.all_reduce(self._fence, group=self.group)      # stream-ordered completion fence
+            return
         for (r_off, nr) in p.chunks:
             if nr == 0:
                 continue
@@ -111,19 +206,29 @@ class ShardedMap:
             own = max(0, min(r_off + nr, p.nrows) - r_off)      # rows of this chunk this rank owns
             if own:
                 oc = own * nx
-                map_device(s, q, rho, Gamma, x0, y0, dx, dy, nx, p.row0 + r_off, own,
-                           buf["A0"][o:o + oc], buf["A2"][o:o + oc], buf["A4"][o:o + oc],
-                           buf["nimg"][o:o + oc], buf["flags"][o:o + oc], order=order,
-                           stream=cur.cuda_stream, device=self.device.index)
-            if p.world > 1 and gather:
-                self.comm_stream.wait_stream(cur)
-                with t.cuda.stream(self.comm_stream):
-                    for key in ("A0", "A2", "A4", "nimg", "flags"):
+                self._launch(s, q, rho, Gamma, x0, y0, dx, dy, p.row0 + r_off, own,
+                             {k: v[o:o + oc] for k, v in buf.items()}, order, stream)
+            if p.world > 1 and gather and self.gather == "nccl":
+                if self.comm_stream is not None:
+                    self.comm_stream.wait_stream(cur)
+                with (t.cuda.stream(self.comm_stream) if self.comm_stream is not None else _null()):
+                    for key, _ in KEYS:
                         src = buf[key][o:o + cnt]
                         dst = [self.full[r][key][o:o + cnt] for r in range(p.world)] if p.rank == 0 else None
                         dist.gather(src, dst, dst=0, group=self.group)
-        if p.world > 1 and gather:
+        if p.world > 1 and gather and self.comm_stream is not None:
             cur.wait_stream(self.comm_stream)
+
+    def full_views(self):
+        """Rank 0: {key: (ny, nx) tensor} of the whole map without a copy (p2p / single rank), else None."""
+        p = self.plan
+        if p.rank != 0:
+            return None
+        if self.gather == "p2p" and p.world > 1:
+            return {k: v.view(self.ny, self.nx) for k, v in self.full_map.items()}
+        if p.world == 1:
+            return {k: v[: self.ny * self.nx].view(self.ny, self.nx) for k, v in self.local.items()}
+        return None
 
     def assemble_host(self):
         """Rank 0: the full (ny, nx) arrays on the host (numpy), from the gathered shards."""
@@ -131,12 +236,23 @@ class ShardedMap:
         p, nx = self.plan, self.nx
         if p.rank != 0:
             return None
+        fv = self.full_views()
+        if fv is not None:
+            return {k: v.cpu().numpy() for k, v in fv.items()}
         out = {}
-        for key in ("A0", "A2", "A4", "nimg", "flags"):
+        for key, _ in KEYS:
             parts = []
             for r in range(p.world):
                 lo, hi = shard_range(self.ny, r, p.world, self.align)
-                src = self.local if (p.world == 1 or r == 0) else self.full[r]
+                src = self.local if r == 0 else self.full[r]
                 parts.append(src[key][:(hi - lo) * nx].cpu().numpy().reshape(hi - lo, nx))
             out[key] = np.concatenate(parts, axis=0)
         return out
+
+
+class _null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False

@@ -4,6 +4,8 @@ with the oracle / the golden vectors of the live reference.  Tolerance: 1e-9 rel
 import io
 import contextlib
 
+import os
+
 import numpy as np
 import pytest
 
@@ -264,6 +266,69 @@ def test_device_pointer_api_and_sharded_map(mb):
     host = mb.magnification_map(s, q, rho, G, x0, y0, dx, dy, nx, ny)
     for k in ("A0", "A2", "A4", "nimg", "flags"):
         assert np.array_equal(dev[k], host[k]), k
+
+
+def test_output_selection(mb):
+    """NULL outputs in the C ABI: unselected arrays are neither stored nor copied; the others are unchanged."""
+    s, q, rho, G = 1.0, 0.5, 1e-3, 0.5
+    nx = ny = 96
+    x0, y0, dx, dy = -0.88, -0.8, 1.6 / nx, 1.6 / ny
+    full = mb.magnification_map(s, q, rho, G, x0, y0, dx, dy, nx, ny)
+    part = mb.magnification_map(s, q, rho, G, x0, y0, dx, dy, nx, ny, outputs=("A4", "nimg"))
+    assert set(part) == {"A4", "nimg"}
+    assert np.array_equal(part["A4"], full["A4"]) and np.array_equal(part["nimg"], full["nimg"])
+    zeta = mb.map_coordinates(s, q, x0, y0, dx, dy, nx, ny)
+    pp = mb.magnification_points(s, q, rho, G, zeta, outputs=("A0", "flags"))
+    pf = mb.magnification_points(s, q, rho, G, zeta)
+    assert np.array_equal(pp["A0"], pf["A0"]) and np.array_equal(pp["flags"], pf["flags"])
+    with pytest.raises(ValueError):
+        mb.magnification_map(s, q, rho, G, x0, y0, dx, dy, nx, ny, outputs=())
+
+
+def _two_gpu_worker(rank, world, port, gather, out_dir):
+    import torch
+    import torch.distributed as dist
+    os.environ["MLM_DEVICE"] = str(rank)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    try:
+        from microlensing_b200.sharding import ShardedMap
+        s, q, rho, G = 1.0, 0.5, 1e-3, 0.5
+        nx, ny = 512, 320
+        x0, y0, dx, dy = -0.88, -0.8, 1.6 / nx, 1.6 / ny
+        sm = ShardedMap(nx, ny, rank, world, gather=gather)
+        for _ in range(2):
+            sm.compute(s, q, rho, G, x0, y0, dx, dy)
+        torch.cuda.synchronize()
+        full = sm.assemble_host()
+        if rank == 0:
+            np.savez(os.path.join(out_dir, f"full_{gather}.npz"), **full)
+        dist.barrier()
+        sm.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("gather", ["p2p", "nccl"])
+def test_two_gpu_sharded_map_equals_single_gpu(mb, tmp_path, gather):
+    """Row-sharded over 2 GPUs with the fused peer-store gather (and the NCCL gather): rank 0's
+    assembled map is bit-identical to the single-GPU map."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    mp.spawn(_two_gpu_worker, args=(2, port, gather, str(tmp_path)), nprocs=2, join=True)
+    got = np.load(tmp_path / f"full_{gather}.npz")
+    s, q, rho, G = 1.0, 0.5, 1e-3, 0.5
+    nx, ny = 512, 320
+    one = mb.magnification_map(s, q, rho, G, -0.88, -0.8, 1.6 / nx, 1.6 / ny, nx, ny)
+    for k in ("A0", "A2", "A4", "nimg", "flags"):
+        assert np.array_equal(got[k], one[k]), k
 
 
 def test_full_size_properties(mb):

@@ -1,9 +1,13 @@
 #!/usr/bin/env python
 """Summarise an .ncu-rep (ncu --set full) into a small CSV + markdown table for profiles/.
 
-    python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r1_name [positions_per_launch]
+    python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r1_name [positions_per_launch [executed.json]]
+
+With the 4th argument the executed-work figures of the LAST launch are also written as JSON
+(profiles/k_map_executed.json is what bench.py reads for roofline.executed / roofline.traffic).
 """
 import csv
+import json
 import subprocess
 import sys
 
@@ -78,6 +82,19 @@ def main():
                    f"executed flop per position (2 DFMA + DMUL + DADD): {flop / npos:.0f}",
                    f"executed FP64 rate under ncu: {flop / dur / 1e12:.2f} TFLOP/s; "
                    f"positions/s under ncu: {npos / dur:.3e}"]
+            if len(sys.argv) > 4:
+                def tobytes(k):
+                    u = units[idx[k]].lower()
+                    return f(k) * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
+                js = {"kernel": data[-1][name_i] if name_i is not None else None, "positions_per_launch": npos,
+                      "fp64_inst_per_position": (dfma + dmul + dadd) / npos,
+                      "dfma_dmul_dadd_per_position": [dfma / npos, dmul / npos, dadd / npos],
+                      "flop_per_position": flop / npos,
+                      "fp64_pipe_pct": f("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
+                      "registers_per_thread": f("launch__registers_per_thread"),
+                      "dram_bytes_per_launch": tobytes("dram__bytes_read.sum") + tobytes("dram__bytes_write.sum"),
+                      "duration_ms_under_ncu": dur * 1e3, "source": out + ".md"}
+                json.dump(js, open(sys.argv[4], "w"), indent=1)
         except Exception as e:  # noqa
             md.append(f"(derived numbers unavailable: {e})")
     open(out + ".csv", "w").write("\n".join(lines) + "\n")
