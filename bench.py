@@ -408,14 +408,76 @@ def bench_b200(args):
                 "api": "microlensing_b200.magnification_map (host buffers, pinned; D2H inside the call)"},
         "gpu_launches": int(launches), "clocks": clocks,
         "kernel_only": {"value": kernel_rate, "ms_per_step": ms_kernel},
-        "flagged_positions_rank0": flag_any,
+        "flagged_positions": flag_any,
     }
+    if world == 1 and not args.no_other:
+        line["other_configs"] = other_configs(mb, dev)
     print(json.dumps(line))
     if world > 1:
         sm.close()
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def other_configs(mb, dev, reps=3):
+    """Device-resident kernel timings of the other BASELINE.json configurations (parity-test cases, not
+    the headline): CUDA events around `reps` launches after one warm-up, outputs resident in HBM."""
+    import torch
+    from microlensing_b200.batched import map_device, models_device, points_device, lightcurve_coordinates
+    st = torch.cuda.current_stream().cuda_stream
+    out = {}
+
+    def bufs(n):
+        return ([torch.empty(n, dtype=torch.float64, device=dev) for _ in range(3)]
+                + [torch.empty(n, dtype=torch.uint8, device=dev) for _ in range(2)])
+
+    def timed(fn, n, label, extra=None):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        out[label] = dict(positions=n, ms=ms, mags_per_s=n / (ms * 1e-3), **(extra or {}))
+
+    c = CONFIGS["C3"]
+    x0, y0, dx, dy = map_window(c)
+    n = c["nx"] * c["ny"]
+    b = bufs(n)
+    timed(lambda: map_device(c["s"], c["q"], c["rho"], c["Gamma"], x0, y0, dx, dy, c["nx"], 0, c["ny"], *b, stream=st),
+          n, "C3_map_4096", {"kernel": "k_map<4>", "f5": None})
+    out["C3_map_4096"]["f5"] = float((b[3] == 5).float().mean())
+
+    c = CONFIGS["C2"]
+    T = c["T"]
+    dtau = (c["tau1"] - c["tau0"]) / T
+    b = bufs(T)
+    par = [torch.tensor([c[k]], dtype=torch.float64, device=dev) for k in ("s", "q", "rho", "Gamma", "u0", "alpha")]
+    timed(lambda: models_device(*par, 1, c["tau0"], dtau, T, *b, stream=st), T, "C2_lightcurve_1e6_tracked",
+          {"kernel": "k_models<4> (in-kernel trajectory, warm-started segments)"})
+    zeta = torch.from_numpy(lightcurve_coordinates(c["s"], c["q"], c["u0"], c["alpha"], c["tau0"], dtau, T)).to(dev)
+    timed(lambda: points_device(c["s"], c["q"], c["rho"], c["Gamma"], zeta, T, *b, stream=st), T,
+          "C2_lightcurve_1e6_points", {"kernel": "k_points<4> (arbitrary positions, cold solve each)"})
+
+    c = CONFIGS["C5"]
+    rng = np.random.default_rng(c["seed"])
+    M, T = c["M"], c["T"]
+    sv = np.exp(rng.uniform(np.log(0.5), np.log(2.), M))
+    qv = np.exp(rng.uniform(np.log(1e-4), np.log(1.), M))
+    rv = np.exp(rng.uniform(np.log(1e-4), np.log(1e-2), M))
+    gv = np.full(M, 0.5)
+    uv, av = rng.uniform(-.5, .5, M), rng.uniform(0, 2 * np.pi, M)
+    par = [torch.from_numpy(a).to(dev) for a in (sv, qv, rv, gv, uv, av)]
+    b = bufs(M * T)
+    timed(lambda: models_device(*par, M, -2.0, 4.0 / T, T, *b, stream=st), M * T, "C5_models_1e4x2000",
+          {"kernel": "k_models<4>", "f5": None})
+    out["C5_models_1e4x2000"]["f5"] = float((b[3] == 5).float().mean())
+    out["C5_models_1e4x2000"]["noconv_flags"] = int((b[4] & 1).sum())
+    return out
 
 
 def _executed_profile():
@@ -447,6 +509,7 @@ def main():
     ap.add_argument("--chunks", type=int, default=0, help="row chunks per rank (0: 1, or 4 with --gather nccl)")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"], help="N>1: how the shards reach rank 0")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-other", action="store_true", help="skip the kernel timings of C2/C3/C5")
     ap.add_argument("--cpu-per-core", type=int, default=6000)
     ap.add_argument("--ref-per-core", type=int, default=6000)
     args = ap.parse_args()

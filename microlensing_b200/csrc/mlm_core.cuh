@@ -188,9 +188,12 @@ MLM_HD void lens_polynomial(const LensTable& T, cd zeta, cd c[6]) {
 #endif
 #define MLM_EPS 1.1102230246251565e-16               /* 2^-53 */
 #define MLM_LAG_MAXIT 64
-// Newton on the quintic stops once a step is below 1e-6 |z|: by quadratic convergence the root is
-// then good to ~K 1e-12 |z| (K = |p''/2p'|), enough for the 1e-6 residual test; the physical
-// images are subsequently polished on the lens equation itself to rounding level.
+// Newton on the quintic stops once a step is below 1e-6 d, d = distance of the root to the nearer
+// lens: by quadratic convergence the root is then good to ~K (1e-6 d)^2 with K = |p''/2p'| ~ 1/d
+// (the roots cluster around the lenses on that scale; relative to |z| alone the rule fails next to
+// a low-mass secondary, where d ~ sqrt(q) and the residual test amplifies root errors by q/d^2).
+// That is enough for the 1e-6 residual test; the physical images are subsequently polished on
+// the lens equation itself to rounding level.
 #define MLM_NEWTON_TOL2 1e-12
 #ifndef MLM_FLAG_NOCONV          /* same values as include/mlmultipoles.h */
 #define MLM_FLAG_NOCONV 1        /* an iteration cap was hit */
@@ -202,6 +205,17 @@ MLM_HD void lens_polynomial(const LensTable& T, cd zeta, cd c[6]) {
 #endif
 
 MLM_HD double mag1(cd a) { return fabs(a.x) + fabs(a.y); }   // |a| <= mag1 <= sqrt2 |a|
+
+// Stopping rule of the Newton iterations on the quintic (see MLM_NEWTON_TOL2): the step is below
+// 1e-6 of the distance to the nearer lens (floor 1e-10 |z|), or the iteration has reached the
+// rounding noise of the polynomial evaluation (a step that is already below 1e-7 |z| and no longer
+// shrinks: clustered roots next to a secondary of q <~ 1e-5 carry ~1e-9 of noise).
+MLM_HD bool newton_stop(double dz2, double prev_dz2, cd z, double s) {
+    const double xs = z.x + s;
+    const double z2 = norm2(z);
+    const double d2 = fmin(z2, fma(xs, xs, z.y * z.y));
+    return (dz2 <= fmax(MLM_NEWTON_TOL2 * d2, 1e-20 * z2)) || (dz2 >= 0.25 * prev_dz2 && dz2 <= 1e-14 * z2);
+}
 
 // p, p' at x for the full quintic
 MLM_HD void horner2(const cd c[6], cd x, cd& p, cd& dp) {
@@ -219,7 +233,7 @@ MLM_HD void horner2(const cd c[6], cd x, cd& p, cd& dp) {
 // Laguerre iterations from x=0 on the successively deflated polynomial (kept zero-padded in
 // d[0..5] so one code path serves every degree), closed form for the last two roots, then
 // Newton polishing of every root on the undeflated polynomial.
-MLM_HD int solve_roots(const cd c[6], cd z[5], unsigned& flags) {
+MLM_HD int solve_roots(const cd c[6], double s, cd z[5], unsigned& flags) {
     cd d[6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) d[k] = c[k];
@@ -320,6 +334,7 @@ MLM_HD int solve_roots(const cd c[6], cd z[5], unsigned& flags) {
     for (int k = 0; k < 5; ++k) {
         if (k < deg0) {
             cd zk = z[k];
+            double prev = 1e300;
 #pragma unroll 1
             for (int j = 0; j < 4; ++j) {
                 cd p, dp;
@@ -329,7 +344,8 @@ MLM_HD int solve_roots(const cd c[6], cd z[5], unsigned& flags) {
                 const double dz2 = norm2(dz);
                 if (!(dz2 < 1e300)) break;            // p'=0 or overflow: keep the deflated root
                 zk = zk - dz;
-                if (dz2 <= MLM_NEWTON_TOL2 * norm2(zk)) break;
+                if (newton_stop(dz2, prev, zk, s)) break;
+                prev = dz2;
                 if (j == 3) flags |= MLM_FLAG_NOCONV;
             }
             z[k] = zk;
@@ -345,7 +361,7 @@ MLM_HD int solve_roots(const cd c[6], cd z[5], unsigned& flags) {
 // converged and the five results are five DISTINCT roots (Vieta: sum z_k = -c4/c5; two tracks
 // collapsing onto one root, the failure mode next to a caustic, breaks the sum by their
 // separation).  The accepted roots satisfy the same stopping rule as the cold path's polish.
-MLM_HD bool track_roots(const cd c[6], cd z[5]) {
+MLM_HD bool track_roots(const cd c[6], double s, cd z[5]) {
     if (c[5].x == 0.0 && c[5].y == 0.0) return false;
     bool ok = true;
     cd sum = mk(0.0, 0.0);
@@ -354,6 +370,7 @@ MLM_HD bool track_roots(const cd c[6], cd z[5]) {
     for (int k = 0; k < 5; ++k) {
         cd zk = z[k];
         bool conv = false;
+        double prev = 1e300;
 #pragma unroll 1
         for (int j = 0; j < 6; ++j) {
             cd p, dp;
@@ -363,7 +380,8 @@ MLM_HD bool track_roots(const cd c[6], cd z[5]) {
             const double dz2 = norm2(dz);
             if (!(dz2 < 1e300)) break;
             zk = zk - dz;
-            if (dz2 <= MLM_NEWTON_TOL2 * norm2(zk)) { conv = true; break; }
+            if (newton_stop(dz2, prev, zk, s)) { conv = true; break; }
+            prev = dz2;
         }
         ok = ok && conv;
         z[k] = zk;
@@ -380,7 +398,7 @@ MLM_HD bool track_roots(const cd c[6], cd z[5]) {
 // 1: warm start from sz, 2: warm start from the linear extrapolation 2 sz - szp, which cuts the
 // initial error from O(h) to O(h^2) and the Newton work to ~1 step per root).  Falls back to
 // the cold solve whenever tracking is rejected.  Returns the new hist.
-MLM_HD int advance_roots(const cd c[6], cd* sz, cd* szp, int stride, int hist, unsigned& flags) {
+MLM_HD int advance_roots(const cd c[6], double s, cd* sz, cd* szp, int stride, int hist, unsigned& flags) {
     cd z[5];
     if (hist >= 1) {
 #pragma unroll
@@ -394,14 +412,14 @@ MLM_HD int advance_roots(const cd c[6], cd* sz, cd* szp, int stride, int hist, u
             szp[k * stride] = zc;
             z[k] = pred;
         }
-        if (track_roots(c, z)) {
+        if (track_roots(c, s, z)) {
 #pragma unroll
             for (int k = 0; k < 5; ++k) sz[k * stride] = z[k];
             return 2;
         }
         MLM_COUNT(track_fallbacks);
     }
-    const int deg = solve_roots(c, z, flags);
+    const int deg = solve_roots(c, s, z, flags);
 #pragma unroll
     for (int k = 0; k < 5; ++k) sz[k * stride] = z[k];
     return deg == 5 ? 1 : 0;
@@ -524,36 +542,37 @@ MLM_HD void accumulate_images(const LensTable& T, const SourceFactors sf, cd zet
         cd f = zk - zeta - conj(W1);
         const double f2 = norm2(f);
         if (f2 > 1e-14 && f2 < 1e-10) flags |= MLM_FLAG_AMBIG;
-        if (!(f2 < 1e-8)) continue;                   // NaN residual -> rejected, like NumPy
+        if (!(f2 < 1e-2)) continue;                   // NaN residual -> rejected, like NumPy
         // Newton on the lens equation z - zeta - conj(W1(z)) = 0 (well conditioned, unlike the
         // polynomial at small q):  dz = -(f + conj(W2) conj(f)) / (1 - |W2|^2)
         bool phys = (f2 < 1e-12);                     // the reference's test, multipoles.py:183
+        // physical root: only ever a tiny correction.  Residual in (1e-6, 1e-1): the root noise of
+        // an ill-conditioned polynomial, amplified by |W2| up to 1e7 (faint image next to a low-mass
+        // lens), can push a true image over the threshold; it is kept iff Newton on the lens
+        // equation, started with a minute step (< 1e-7), converges (each step >= 100x smaller than
+        // the one before, down to 1e-10 of the distance to the nearer lens).
+        bool conv = false;
+        double lim = phys ? 1e-10 : 1e-14;
 #pragma unroll 1
-        for (int it = 0; it < 2; ++it) {
+        for (int it = 0; it < 3; ++it) {
             const cd r1s = csq(r1), r2s = csq(r2);
             const cd W2 = rfma(T.alpha[2], r1s, scale(T.beta[2], r2s));
             const double iJ = rcp(1.0 - norm2(W2));
             const cd dz = scale(-iJ, cjfma(W2, conj(f), f));
             const double dz2 = norm2(dz);
-            // physical root: only ever a tiny correction.  Residual in (1e-6, 1e-4): the root
-            // noise of an ill-conditioned polynomial, amplified by |W2| >> 1 (faint image next
-            // to a low-mass lens), can push a true image over the threshold; it is kept iff a
-            // minute Newton step (< 1e-8) lands on an exact solution.
-            if (!(dz2 < (phys ? 1e-10 : 1e-16))) break;
+            // (8 ulp of |z|)^2: steps at the rounding level of z count as converged, not as stalled
+            const double ulp2 = 3.2e-30 * norm2(zk);
+            if (!(dz2 < fmax(lim, ulp2))) break;
             zk = zk + dz;
             zs = mk(zk.x + T.s, zk.y);
             r1 = crcp(zk);
             r2 = crcp(zs);
-            // a second step only when the first one was not already below 1e-10 |z| (its
-            // quadratic remainder could then exceed rounding) or the root is being rescued
-            if (phys && dz2 <= 1e-20 * norm2(zk)) break;
+            if (dz2 <= fmax(1e-20 * fmin(norm2(zk), norm2(zs)), ulp2)) { conv = true; break; }
+            lim = 1e-4 * dz2;
             W1 = rfma(T.alpha[1], r1, scale(T.beta[1], r2));
             f = zk - zeta - conj(W1);
-            if (!phys) {
-                phys = (norm2(f) < 1e-18);
-                break;
-            }
         }
+        if (!phys) phys = conv;
         if (!phys) continue;
         ++n;
         // W_k = alpha_k r1^k + beta_k r2^k, multipoles.py:197-201
@@ -589,7 +608,7 @@ MLM_HD PointResult point_magnification(const LensTable& T, const SourceFactors s
     PointResult out;
     out.flags = 0;
     lens_polynomial(T, zeta, c);
-    solve_roots(c, z, out.flags);
+    solve_roots(c, T.s, z, out.flags);
     accumulate_images<ORDER>(T, sf, zeta, z, 1, out);
     return out;
 }

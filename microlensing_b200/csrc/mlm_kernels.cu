@@ -58,7 +58,7 @@ k_points(const __grid_constant__ LensTable T, const SourceFactors sf, const doub
     PointResult r;
     r.flags = 0;
     lens_polynomial(T, zt, c);
-    advance_roots(c, sz, sz, MLM_BLOCK, 0, r.flags);  // hist = 0: cold solve
+    advance_roots(c, T.s, sz, sz, MLM_BLOCK, 0, r.flags);  // hist = 0: cold solve
     accumulate_images<ORDER>(T, sf, zt, sz, MLM_BLOCK, r);
     store_result(r, i, A0, A2, A4, nimg, flags);
 }
@@ -97,24 +97,33 @@ k_map(const __grid_constant__ LensTable T, const SourceFactors sf, double x0, do
             PointResult res;
             res.flags = 0;
             lens_polynomial(T, zeta, c);
-            hist = advance_roots(c, sz, szp, MLM_BLOCK, hist, res.flags);
+            hist = advance_roots(c, T.s, sz, szp, MLM_BLOCK, hist, res.flags);
             accumulate_images<ORDER>(T, sf, zeta, sz, MLM_BLOCK, res);
             store_result(res, (r - row0) * nx + col, A0, A2, A4, nimg, flags);
         }
     }
 }
 
-// K1c: batched model grid; blockIdx.y = model, the block stages that model's table in shared
-// memory, threads run over epochs.
+// K1c: batched model grid / light curves.  blockIdx.y strides over models; the block stages that
+// model's table in shared memory.  Each thread owns a SEGMENT of `seg` consecutive epochs of the
+// straight trajectory and walks along it with warm-started root tracking (cold solve at the
+// segment start and wherever tracking is rejected), exactly like a map column in k_map.
+// seg depends only on the number of epochs, so sharding the models over ranks does not change
+// a single bit of any model's light curve.
+#define MLM_MODELS_BLOCK 64
 template <int ORDER>
-__global__ void __launch_bounds__(MLM_BLOCK)
+__global__ void __launch_bounds__(MLM_MODELS_BLOCK, 6)
 k_models(const double* __restrict__ s, const double* __restrict__ q, const double* __restrict__ rho,
          const double* __restrict__ Gamma, const double* __restrict__ u0, const double* __restrict__ alpha,
-         int64_t M, double tau0, double dtau, int64_t Tn, double* __restrict__ A0, double* __restrict__ A2,
-         double* __restrict__ A4, uint8_t* __restrict__ nimg, uint8_t* __restrict__ flags) {
+         int64_t M, double tau0, double dtau, int64_t Tn, int seg, double* __restrict__ A0,
+         double* __restrict__ A2, double* __restrict__ A4, uint8_t* __restrict__ nimg, uint8_t* __restrict__ flags) {
     __shared__ LensTable T;
     __shared__ SourceFactors sf;
     __shared__ double rot[3];                          // cos(alpha), sin(alpha), shift
+    __shared__ cd s_roots[2][5][MLM_MODELS_BLOCK];
+    cd* const sz = &s_roots[0][0][threadIdx.x];
+    cd* const szp = &s_roots[1][0][threadIdx.x];
+    const int64_t nseg = (Tn + seg - 1) / seg;
     for (int64_t m = blockIdx.y; m < M; m += gridDim.y) {
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -127,13 +136,29 @@ k_models(const double* __restrict__ s, const double* __restrict__ q, const doubl
         }
         __syncthreads();
         const double u = u0[m];
-        for (int64_t t = (int64_t)blockIdx.x * MLM_BLOCK + threadIdx.x; t < Tn; t += (int64_t)gridDim.x * MLM_BLOCK) {
-            const double tau = __dadd_rn(tau0, __dmul_rn((double)t, dtau));
-            // zeta_cm = (tau + i u0) (cos a + i sin a), then shift to the primary frame
-            const double zx = __dadd_rn(__dadd_rn(__dmul_rn(tau, rot[0]), -__dmul_rn(u, rot[1])), -rot[2]);
-            const double zy = __dadd_rn(__dmul_rn(tau, rot[1]), __dmul_rn(u, rot[0]));
-            const PointResult r = point_magnification<ORDER>(T, sf, mk(zx, zy));
-            store_result(r, m * Tn + t, A0, A2, A4, nimg, flags);
+        const double ur1 = __dmul_rn(u, rot[1]), ur0 = __dmul_rn(u, rot[0]);
+        for (int64_t sg = (int64_t)blockIdx.x * MLM_MODELS_BLOCK + threadIdx.x; sg < nseg;
+             sg += (int64_t)gridDim.x * MLM_MODELS_BLOCK) {
+            const int64_t t0 = sg * seg;
+            const int64_t t1 = (t0 + seg < Tn) ? t0 + seg : Tn;
+            int hist = 0;
+            for (int64_t t = t0; t < t1; ++t) {
+                // compiler barrier: the table is re-read from shared memory where it is used instead of
+                // being hoisted out of the loop into ~40 live registers
+                asm volatile("" ::: "memory");
+                const double tau = __dadd_rn(tau0, __dmul_rn((double)t, dtau));
+                // zeta_cm = (tau + i u0) (cos a + i sin a), then shift to the primary frame
+                const double zx = __dadd_rn(__dadd_rn(__dmul_rn(tau, rot[0]), -ur1), -rot[2]);
+                const double zy = __dadd_rn(__dmul_rn(tau, rot[1]), ur0);
+                const cd zeta = mk(zx, zy);
+                cd c[6];
+                PointResult res;
+                res.flags = 0;
+                lens_polynomial(T, zeta, c);
+                hist = advance_roots(c, T.s, sz, szp, MLM_MODELS_BLOCK, hist, res.flags);
+                accumulate_images<ORDER>(T, sf, zeta, sz, MLM_MODELS_BLOCK, res);
+                store_result(res, m * Tn + t, A0, A2, A4, nimg, flags);
+            }
         }
     }
 }
@@ -147,7 +172,7 @@ k_solve(const __grid_constant__ LensTable T, const double2* __restrict__ zeta, i
     cd c[6], z[5];
     unsigned fl = 0;
     lens_polynomial(T, mk(zz.x, zz.y), c);
-    solve_roots(c, z, fl);
+    solve_roots(c, T.s, z, fl);
 #pragma unroll
     for (int k = 0; k < 5; ++k) roots[5 * i + k] = make_double2(z[k].x, z[k].y);
 }
@@ -236,6 +261,7 @@ struct mlm_context {
     std::string err;
     int sm_count = 148;
     int map_strip = 64;                                // rows per warm-start strip of k_map (MLM_MAP_STRIP)
+    int models_segment = 0;                            // epochs per warm-start segment of k_models (0: from T; MLM_SEGMENT)
 };
 
 static std::string g_err;
@@ -322,6 +348,10 @@ int mlm_create(int device, mlm_context** out) {
     if (const char* e2 = getenv("MLM_MAP_STRIP")) {
         const int v = atoi(e2);
         if (v >= 1 && v <= 4096) ctx->map_strip = v;
+    }
+    if (const char* e3 = getenv("MLM_SEGMENT")) {
+        const int v = atoi(e3);
+        if (v >= 1 && v <= 65536) ctx->models_segment = v;
     }
     *out = ctx;
     return 0;
@@ -476,14 +506,18 @@ int mlm_models(mlm_context* ctx, const double* s, const double* q, const double*
     if (!s || !q || !rho || !Gamma || !u0 || !alpha || !(A0 || A2 || A4 || nimg || flags))
         return fail(ctx, MLM_EINVAL, "mlm_models: NULL buffer");
     DeviceGuard g(ctx->device);
-    int64_t bx = (Tn + MLM_BLOCK - 1) / MLM_BLOCK;
-    if (bx > 1024) bx = 1024;
+    // epochs per warm-start segment: a function of Tn only (see k_models)
+    int seg = ctx->models_segment > 0 ? ctx->models_segment : (int)((Tn + MLM_MODELS_BLOCK - 1) / MLM_MODELS_BLOCK);
+    if (ctx->models_segment <= 0) seg = seg < 4 ? 4 : (seg > 32 ? 32 : seg);
+    const int64_t nseg = (Tn + seg - 1) / seg;
+    int64_t bx = (nseg + MLM_MODELS_BLOCK - 1) / MLM_MODELS_BLOCK;
+    if (bx > 4096) bx = 4096;
     dim3 grid((unsigned)bx, (unsigned)(M < 65535 ? M : 65535));
     cudaStream_t st = pick(ctx, stream);
     if (order == 4)
-        k_models<4><<<grid, MLM_BLOCK, 0, st>>>(s, q, rho, Gamma, u0, alpha, M, tau0, dtau, Tn, A0, A2, A4, nimg, flags);
+        k_models<4><<<grid, MLM_MODELS_BLOCK, 0, st>>>(s, q, rho, Gamma, u0, alpha, M, tau0, dtau, Tn, seg, A0, A2, A4, nimg, flags);
     else
-        k_models<2><<<grid, MLM_BLOCK, 0, st>>>(s, q, rho, Gamma, u0, alpha, M, tau0, dtau, Tn, A0, A2, A4, nimg, flags);
+        k_models<2><<<grid, MLM_MODELS_BLOCK, 0, st>>>(s, q, rho, Gamma, u0, alpha, M, tau0, dtau, Tn, seg, A0, A2, A4, nimg, flags);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;

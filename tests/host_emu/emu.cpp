@@ -36,7 +36,7 @@ void emu_roots(double s, double q, const double* zeta, long n, double* roots, un
         cd c[6], z[5];
         unsigned fl = 0;
         lens_polynomial(T, mk(zeta[2 * i], zeta[2 * i + 1]), c);
-        solve_roots(c, z, fl);
+        solve_roots(c, T.s, z, fl);
         for (int k = 0; k < 5; ++k) { roots[10 * i + 2 * k] = z[k].x; roots[10 * i + 2 * k + 1] = z[k].y; }
         flags[i] = (unsigned char)fl;
     }
@@ -81,7 +81,7 @@ extern "C" void emu_strip(double s, double q, double rho, double Gamma, const do
         r.flags = 0;
         lens_polynomial(T, zeta_i, c);
         const int before = hist;
-        hist = advance_roots(c, z, zp, 1, hist, r.flags);
+        hist = advance_roots(c, T.s, z, zp, 1, hist, r.flags);
         if (before == 0 || hist < 2) ++cold;
         accumulate_images<4>(T, sf, zeta_i, z, 1, r);
         A0[i] = r.A0; A2[i] = r.A2; A4[i] = r.A4;

@@ -151,6 +151,20 @@ def emu(built):
             return r, fl
 
         @staticmethod
+        def strip(s, q, rho, G, zeta, seg):
+            """warm-started segments of `seg` consecutive positions: control flow of k_map / k_models"""
+            zeta = np.ascontiguousarray(zeta, dtype=np.complex128)
+            n = zeta.size
+            A = [np.zeros(n) for _ in range(3)]
+            ni, fl = np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+            ncold = ctypes.c_long(0)
+            lib.emu_strip(ctypes.c_double(s), ctypes.c_double(q), ctypes.c_double(rho), ctypes.c_double(G),
+                          zeta.view(np.float64).ctypes.data_as(dp), ctypes.c_long(n), ctypes.c_int(seg),
+                          *[a.ctypes.data_as(dp) for a in A], ni.ctypes.data_as(up), fl.ctypes.data_as(up),
+                          ctypes.byref(ncold))
+            return ni, np.stack(A, 1), fl, ncold.value
+
+        @staticmethod
         def image_terms(W, literal):
             W = np.ascontiguousarray(W, dtype=np.complex128)
             out = np.zeros((W.shape[0], 3))
@@ -223,3 +237,41 @@ def test_logic_degenerate_positions(emu):
     ni, A, fl = emu.points(1.0, 0.5, 1e-3, 0.5, np.array([0j, -1 + 0j, 1e-9 + 0j]))
     assert list(ni) == [3, 3, 3]
     assert np.allclose(A[0], [5.45344087, 5.45340883, 5.45340883], rtol=1e-8)
+
+
+def test_logic_warm_started_tracking_equals_cold_solves(emu):
+    """k_map / k_models walk a column / a light curve with warm-started root tracking; the cold solve
+    of every position (validated against the reference above) must give the same image counts and
+    the same values to rounding -- on map columns of C3/C4 and on C5-like random models (q >= 1e-4)
+    at the pitch of the C5 light curves, including the short segments of a 400-epoch curve."""
+    from microlensing_b200.batched import lightcurve_coordinates
+    worst, cold, tot = 0.0, 0, 0
+    rng = np.random.default_rng(7)
+    cases = []
+    for (s, q, cx, half, nx) in ((1.0, 0.5, -0.08, 0.8, 8192), (0.8, 0.1, 0.11, 0.75, 4096)):
+        dy = 2 * half / nx
+        y = -half + (np.arange(nx // 4, 3 * nx // 4) + 0.5) * dy          # central half of the column
+        for c in rng.integers(0, nx, 3):
+            x = (cx - half + (c + 0.5) * dy) - s * q / (1 + q)
+            cases.append((s, q, 1e-3, x + 1j * y, 64))
+    M = 40
+    sv = np.exp(rng.uniform(np.log(0.5), np.log(2.), M))
+    qv = np.exp(rng.uniform(np.log(1e-4), np.log(1.), M))
+    rv = np.exp(rng.uniform(np.log(1e-4), np.log(1e-2), M))
+    uv, av = rng.uniform(-.5, .5, M), rng.uniform(0, 2 * np.pi, M)
+    for m in range(M):
+        T, seg = ((2000, 32) if m % 2 else (400, 7))
+        cases.append((sv[m], qv[m], rv[m], lightcurve_coordinates(sv[m], qv[m], uv[m], av[m], -2.0, 4.0 / T, T), seg))
+    for (s, q, rho, zeta, seg) in cases:
+        ni, A, fl, nc = emu.strip(s, q, rho, 0.5, zeta, seg)
+        n0, B, f0 = emu.points(s, q, rho, 0.5, zeta)
+        assert np.array_equal(ni, n0), (s, q, np.where(ni != n0)[0][:5])
+        ok = (fl == 0) & (f0 == 0)
+        with np.errstate(all="ignore"):
+            rel = np.abs(A / B - 1).max(axis=1)
+        worst = max(worst, rel[ok].max())
+        assert ((fl & 3) == 0).all()
+        cold += nc
+        tot += len(zeta)
+    assert worst < 1e-9, worst
+    assert cold / tot < 0.12          # tracking is accepted almost everywhere (segment starts are cold)
