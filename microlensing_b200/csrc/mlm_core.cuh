@@ -207,14 +207,15 @@ MLM_HD void lens_polynomial(const LensTable& T, cd zeta, cd c[6]) {
 MLM_HD double mag1(cd a) { return fabs(a.x) + fabs(a.y); }   // |a| <= mag1 <= sqrt2 |a|
 
 // Stopping rule of the Newton iterations on the quintic (see MLM_NEWTON_TOL2): the step is below
-// 1e-6 of the distance to the nearer lens (floor 1e-10 |z|), or the iteration has reached the
+// 1e-6 of the distance to the nearer lens, or the iteration has reached the
 // rounding noise of the polynomial evaluation (a step that is already below 1e-7 |z| and no longer
 // shrinks: clustered roots next to a secondary of q <~ 1e-5 carry ~1e-9 of noise).
-MLM_HD bool newton_stop(double dz2, double prev_dz2, cd z, double s) {
+MLM_HD bool newton_stop(double dz2, double prev4, cd z, double s) {   // prev4 = 0.25 * previous dz2
     const double xs = z.x + s;
-    const double z2 = norm2(z);
-    const double d2 = fmin(z2, fma(xs, xs, z.y * z.y));
-    return (dz2 <= fmax(MLM_NEWTON_TOL2 * d2, 1e-20 * z2)) || (dz2 >= 0.25 * prev_dz2 && dz2 <= 1e-14 * z2);
+    const double yy = z.y * z.y;
+    const double z2 = fma(z.x, z.x, yy);
+    const double d2 = fmin(z2, fma(xs, xs, yy));
+    return (dz2 <= MLM_NEWTON_TOL2 * d2) || (dz2 >= prev4 && dz2 <= 1e-14 * z2);
 }
 
 // p, p' at x for the full quintic
@@ -345,7 +346,7 @@ MLM_HD int solve_roots(const cd c[6], double s, cd z[5], unsigned& flags) {
                 if (!(dz2 < 1e300)) break;            // p'=0 or overflow: keep the deflated root
                 zk = zk - dz;
                 if (newton_stop(dz2, prev, zk, s)) break;
-                prev = dz2;
+                prev = 0.25 * dz2;
                 if (j == 3) flags |= MLM_FLAG_NOCONV;
             }
             z[k] = zk;
@@ -381,7 +382,7 @@ MLM_HD bool track_roots(const cd c[6], double s, cd z[5]) {
             if (!(dz2 < 1e300)) break;
             zk = zk - dz;
             if (newton_stop(dz2, prev, zk, s)) { conv = true; break; }
-            prev = dz2;
+            prev = 0.25 * dz2;
         }
         ok = ok && conv;
         z[k] = zk;
