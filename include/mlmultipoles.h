@@ -138,6 +138,10 @@ int mlm_akl_host(mlm_context* ctx, const double* mu, const double* W2, const dou
 /* DFMA-chain microbenchmark: measured FP64 FMA throughput of this GPU in TFLOP/s
  * (2 flop per DFMA), the denominator of the FP64 roofline (MEASURED_PEAKS.json has none). */
 int mlm_fp64_peak(mlm_context* ctx, double* tflops);
+/* FP64-pipe probe with a realistic operand pattern (three distinct register pairs per instruction):
+ * mode 1 = DFMA only, mode 2 = DFMA/DMUL/DADD 11:4:1; blocks_per_sm x 128 threads resident per SM.
+ * Returns executed FP64 thread-instructions per second (nominal B200: 148 x 64 x 1.965e9 = 1.86e13). */
+int mlm_fp64_probe(mlm_context* ctx, int mode, int blocks_per_sm, double* inst_per_s);
 /* static description of the fused kernel (registers per thread, spill bytes) from
  * cudaFuncGetAttributes: [0]=regs points<4>, [1]=local bytes points<4>, [2]=regs map<4>, [3]=local bytes map<4> */
 int mlm_kernel_info(mlm_context* ctx, int32_t* out, int n);

@@ -46,6 +46,7 @@ SIGNATURES = {
     "mlm_akl": [_P, _P, _P, _P, _L, _P, _P],
     "mlm_akl_host": [_P, _P, _P, _P, _L, _P],
     "mlm_fp64_peak": [_P, ctypes.POINTER(_D)],
+    "mlm_fp64_probe": [_P, _I, _I, ctypes.POINTER(_D)],
     "mlm_kernel_info": [_P, ctypes.POINTER(ctypes.c_int32), _I],
 }
 STRING_FUNCS = {"mlm_last_error": [_P], "mlm_version": []}
@@ -115,6 +116,11 @@ class Context:
     def fp64_peak_tflops(self) -> float:
         v = _D(0.0)
         self.check(self.lib.mlm_fp64_peak(self.handle, ctypes.byref(v)), "mlm_fp64_peak")
+        return float(v.value)
+
+    def fp64_probe(self, mode: int, blocks_per_sm: int) -> float:
+        v = _D(0.0)
+        self.check(self.lib.mlm_fp64_probe(self.handle, mode, blocks_per_sm, ctypes.byref(v)), "mlm_fp64_probe")
         return float(v.value)
 
     def kernel_info(self) -> dict:

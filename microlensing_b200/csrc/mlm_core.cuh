@@ -47,6 +47,8 @@ MLM_HD cd scale(double s, cd a) { return mk(s * a.x, s * a.y); }
 MLM_HD double norm2(cd a) { return fma(a.x, a.x, a.y * a.y); }
 // a*b
 MLM_HD cd cmul(cd a, cd b) { return mk(fma(a.x, b.x, -(a.y * b.y)), fma(a.x, b.y, a.y * b.x)); }
+// conj(a)*b
+MLM_HD cd cmulc(cd a, cd b) { return mk(fma(a.x, b.x, a.y * b.y), fma(a.x, b.y, -(a.y * b.x))); }
 // a*a
 MLM_HD cd csq(cd a) { return mk(fma(a.x, a.x, -(a.y * a.y)), 2.0 * (a.x * a.y)); }
 // a*b + c
@@ -78,6 +80,19 @@ MLM_HD double rcp(double a) {
     e = fma(-a, r, 1.0);
     r = fma(r, e, r);
     return r;
+#else
+    return 1.0 / a;
+#endif
+}
+
+// reciprocal good to ~1e-13 relative (one Newton step): for Newton CORRECTIONS, whose own relative
+// accuracy need not exceed the size of the next correction
+MLM_HD double rcp_step(double a) {
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    const double e = fma(-a, r, 1.0);
+    return fma(r, e, r);
 #else
     return 1.0 / a;
 #endif
@@ -362,32 +377,49 @@ MLM_HD int solve_roots(const cd c[6], double s, cd z[5], unsigned& flags) {
 // converged and the five results are five DISTINCT roots (Vieta: sum z_k = -c4/c5; two tracks
 // collapsing onto one root, the failure mode next to a caustic, breaks the sum by their
 // separation).  The accepted roots satisfy the same stopping rule as the cold path's polish.
+MLM_HD cd newton_step(const cd c[6], cd zk, double& dz2) {
+    cd p, dp;
+    horner2(c, zk, p, dp);
+    MLM_COUNT(newton_evals);
+    // dz = p / p' (a NaN from p' = 0 fails every comparison of newton_stop: no convergence -> cold solve)
+    const double idp2 = rcp_step(norm2(dp));
+    const cd dz = scale(idp2, cmulc(dp, p));
+    dz2 = norm2(dz);
+    return zk - dz;
+}
+
 MLM_HD bool track_roots(const cd c[6], double s, cd z[5]) {
     if (c[5].x == 0.0 && c[5].y == 0.0) return false;
+    // First Newton step of all five roots as straight-line code: five independent Horner chains
+    // that the scheduler interleaves (the per-root loops below are serial chains).  With the
+    // extrapolated start ~85 % of the roots are finished after this step.
+    double dz2[5];
+    bool conv[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        z[k] = newton_step(c, z[k], dz2[k]);
+        conv[k] = newton_stop(dz2[k], 1e300, z[k], s);
+    }
     bool ok = true;
     cd sum = mk(0.0, 0.0);
     double mag = 1.0;
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
-        cd zk = z[k];
-        bool conv = false;
-        double prev = 1e300;
+        if (!conv[k]) {
+            cd zk = z[k];
+            double prev = 0.25 * dz2[k];
 #pragma unroll 1
-        for (int j = 0; j < 6; ++j) {
-            cd p, dp;
-            horner2(c, zk, p, dp);
-            MLM_COUNT(newton_evals);
-            const cd dz = cmul(p, crcp(dp));
-            const double dz2 = norm2(dz);
-            if (!(dz2 < 1e300)) break;
-            zk = zk - dz;
-            if (newton_stop(dz2, prev, zk, s)) { conv = true; break; }
-            prev = 0.25 * dz2;
+            for (int j = 0; j < 5; ++j) {
+                double d2;
+                zk = newton_step(c, zk, d2);
+                if (newton_stop(d2, prev, zk, s)) { conv[k] = true; break; }
+                prev = 0.25 * d2;
+            }
+            z[k] = zk;
         }
-        ok = ok && conv;
-        z[k] = zk;
-        sum = sum + zk;
-        mag += norm2(zk);
+        ok = ok && conv[k];
+        sum = sum + z[k];
+        mag += norm2(z[k]);
     }
     const cd v = cfma(c[4], crcp(c[5]), sum);
     return ok && (norm2(v) <= 1e-16 * mag);
@@ -527,23 +559,37 @@ struct PointResult {
 // lens equation itself, and accumulate A0/A2/A4.
 template <int ORDER>
 MLM_HD void accumulate_images(const LensTable& T, const SourceFactors sf, cd zeta, const cd* z, int zstride,
-                              PointResult& out) {
+                              cd* scratch, int sstride, PointResult& out) {
     double A0 = 0.0, A2 = 0.0, A4 = 0.0, minJ = 1e300;
-    unsigned n = 0, flags = out.flags;
-    // The image loop is kept rolled (5 x ~500 instructions would overflow the instruction
-    // cache); the roots are read from memory (shared memory in the kernels) with stride zstride,
-    // so no register array is indexed dynamically and they occupy no registers meanwhile.
+    unsigned n = 0, flags = out.flags, cand = 0;
+    // Pass 1, straight-line over the five roots (five independent reciprocal chains in flight):
+    // residual of the lens equation, multipoles.py:182-183.  1/z and 1/(z+s) go to `scratch`
+    // ([2k], [2k+1] with stride sstride; shared memory in the kernels) for pass 2.
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const cd zk = z[k * zstride];
+        const cd zs = mk(zk.x + T.s, zk.y);
+        const cd r1 = crcp(zk), r2 = crcp(zs);
+        const cd W1 = rfma(T.alpha[1], r1, scale(T.beta[1], r2));
+        const cd f = zk - zeta - conj(W1);
+        const double f2 = norm2(f);
+        scratch[(2 * k) * sstride] = r1;
+        scratch[(2 * k + 1) * sstride] = r2;
+        if (f2 > 1e-14 && f2 < 1e-10) flags |= MLM_FLAG_AMBIG;
+        if (f2 < 1e-2) cand |= 1u << k;               // NaN residual -> rejected, like NumPy
+    }
+    // Pass 2, rolled over the candidates (5 x ~350 instructions would overflow the instruction
+    // cache); roots and reciprocals are read back from memory, so no register array is indexed
+    // dynamically and they occupy no registers meanwhile.
 #pragma unroll 1
     for (int k = 0; k < 5; ++k) {
+        if (!((cand >> k) & 1u)) continue;
         cd zk = z[k * zstride];
         cd zs = mk(zk.x + T.s, zk.y);
-        cd r1 = crcp(zk), r2 = crcp(zs);
-        // residual of the lens equation, multipoles.py:182-183
+        cd r1 = scratch[(2 * k) * sstride], r2 = scratch[(2 * k + 1) * sstride];
         cd W1 = rfma(T.alpha[1], r1, scale(T.beta[1], r2));
         cd f = zk - zeta - conj(W1);
         const double f2 = norm2(f);
-        if (f2 > 1e-14 && f2 < 1e-10) flags |= MLM_FLAG_AMBIG;
-        if (!(f2 < 1e-2)) continue;                   // NaN residual -> rejected, like NumPy
         // Newton on the lens equation z - zeta - conj(W1(z)) = 0 (well conditioned, unlike the
         // polynomial at small q):  dz = -(f + conj(W2) conj(f)) / (1 - |W2|^2)
         bool phys = (f2 < 1e-12);                     // the reference's test, multipoles.py:183
@@ -558,7 +604,7 @@ MLM_HD void accumulate_images(const LensTable& T, const SourceFactors sf, cd zet
         for (int it = 0; it < 3; ++it) {
             const cd r1s = csq(r1), r2s = csq(r2);
             const cd W2 = rfma(T.alpha[2], r1s, scale(T.beta[2], r2s));
-            const double iJ = rcp(1.0 - norm2(W2));
+            const double iJ = rcp_step(1.0 - norm2(W2));
             const cd dz = scale(-iJ, cjfma(W2, conj(f), f));
             const double dz2 = norm2(dz);
             // (8 ulp of |z|)^2: steps at the rounding level of z count as converged, not as stalled
@@ -609,8 +655,9 @@ MLM_HD PointResult point_magnification(const LensTable& T, const SourceFactors s
     PointResult out;
     out.flags = 0;
     lens_polynomial(T, zeta, c);
+    cd scratch[10];
     solve_roots(c, T.s, z, out.flags);
-    accumulate_images<ORDER>(T, sf, zeta, z, 1, out);
+    accumulate_images<ORDER>(T, sf, zeta, z, 1, scratch, 1, out);
     return out;
 }
 

@@ -52,6 +52,7 @@ k_points(const __grid_constant__ LensTable T, const SourceFactors sf, const doub
     if (i >= n) return;
     const double2 zz = __ldg(zeta + i);               // one 16-byte load per thread, coalesced
     __shared__ cd s_roots[5][MLM_BLOCK];
+    __shared__ cd s_rcp[10][MLM_BLOCK];
     cd* const sz = &s_roots[0][threadIdx.x];
     const cd zt = mk(zz.x, zz.y);
     cd c[6];
@@ -59,7 +60,7 @@ k_points(const __grid_constant__ LensTable T, const SourceFactors sf, const doub
     r.flags = 0;
     lens_polynomial(T, zt, c);
     advance_roots(c, T.s, sz, sz, MLM_BLOCK, 0, r.flags);  // hist = 0: cold solve
-    accumulate_images<ORDER>(T, sf, zt, sz, MLM_BLOCK, r);
+    accumulate_images<ORDER>(T, sf, zt, sz, MLM_BLOCK, &s_rcp[0][threadIdx.x], MLM_BLOCK, r);
     store_result(r, i, A0, A2, A4, nimg, flags);
 }
 
@@ -78,6 +79,7 @@ k_map(const __grid_constant__ LensTable T, const SourceFactors sf, double x0, do
     // root store of this thread: current and previous roots, [k][thread] so that a warp touches
     // 512 contiguous bytes per k (conflict-free); keeps 20 doubles out of the register file
     __shared__ cd s_roots[2][5][MLM_BLOCK];
+    __shared__ cd s_rcp[10][MLM_BLOCK];                // 1/z, 1/(z+s) of the five roots (accumulate_images)
     cd* const sz = &s_roots[0][0][threadIdx.x];
     cd* const szp = &s_roots[1][0][threadIdx.x];
     const int64_t col = (int64_t)blockIdx.x * MLM_BLOCK + threadIdx.x;
@@ -98,7 +100,7 @@ k_map(const __grid_constant__ LensTable T, const SourceFactors sf, double x0, do
             res.flags = 0;
             lens_polynomial(T, zeta, c);
             hist = advance_roots(c, T.s, sz, szp, MLM_BLOCK, hist, res.flags);
-            accumulate_images<ORDER>(T, sf, zeta, sz, MLM_BLOCK, res);
+            accumulate_images<ORDER>(T, sf, zeta, sz, MLM_BLOCK, &s_rcp[0][threadIdx.x], MLM_BLOCK, res);
             store_result(res, (r - row0) * nx + col, A0, A2, A4, nimg, flags);
         }
     }
@@ -121,6 +123,7 @@ k_models(const double* __restrict__ s, const double* __restrict__ q, const doubl
     __shared__ SourceFactors sf;
     __shared__ double rot[3];                          // cos(alpha), sin(alpha), shift
     __shared__ cd s_roots[2][5][MLM_MODELS_BLOCK];
+    __shared__ cd s_rcp[10][MLM_MODELS_BLOCK];
     cd* const sz = &s_roots[0][0][threadIdx.x];
     cd* const szp = &s_roots[1][0][threadIdx.x];
     const int64_t nseg = (Tn + seg - 1) / seg;
@@ -156,7 +159,7 @@ k_models(const double* __restrict__ s, const double* __restrict__ q, const doubl
                 res.flags = 0;
                 lens_polynomial(T, zeta, c);
                 hist = advance_roots(c, T.s, sz, szp, MLM_MODELS_BLOCK, hist, res.flags);
-                accumulate_images<ORDER>(T, sf, zeta, sz, MLM_MODELS_BLOCK, res);
+                accumulate_images<ORDER>(T, sf, zeta, sz, MLM_MODELS_BLOCK, &s_rcp[0][threadIdx.x], MLM_MODELS_BLOCK, res);
                 store_result(res, m * Tn + t, A0, A2, A4, nimg, flags);
             }
         }
@@ -244,6 +247,31 @@ __global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, doubl
     }
     const double sum = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
     if (sum == 12345.678) out[0] = sum;               // never true; keeps the chains alive
+}
+
+// FP64-pipe probe with the operand pattern of real code: every instruction reads three DISTINCT
+// register pairs; MODE 1: DFMA only, MODE 2: DFMA/DMUL/DADD mixed 11:4:1, about the mix of k_map.
+template <int MODE>
+__global__ void __launch_bounds__(128, 1) k_fp64_probe(double* out, int iters, const double* __restrict__ in) {
+    double x[8], a[8], b[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { x[k] = in[k] + threadIdx.x; a[k] = in[8 + k]; b[k] = in[16 + k]; }
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (MODE == 1) x[k] = fma(x[k], a[(k + r) & 7], b[(k + 2 * r + 1) & 7]);
+                else if (k < 5 || (k == 7 && (r & 1))) x[k] = fma(x[k], a[(k + r) & 7], b[(k + 2 * r + 1) & 7]);
+                else if (k < 7) x[k] = x[k] * a[(k + r) & 7];
+                else x[k] = x[k] + b[(k + r) & 7];
+            }
+        }
+    }
+    double sum = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sum += x[k];
+    if (sum == 12345.678) out[0] = sum;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -814,6 +842,43 @@ int mlm_fp64_peak(mlm_context* ctx, double* tflops) {
     cudaEventDestroy(e1);
     CK(cudaGetLastError());
     *tflops = best;
+    return 0;
+}
+
+/* experiment: instructions/s of the FP64 pipe under a realistic operand pattern, in units of the
+ * nominal issue rate (fraction of 1 warp-instruction per 2 cycles per SM sub-partition is left to the caller):
+ * returns executed FP64 thread-instructions per second */
+int mlm_fp64_probe(mlm_context* ctx, int mode, int blocks_per_sm, double* inst_per_s) {
+    if (!ctx || !inst_per_s || mode < 1 || mode > 2 || blocks_per_sm < 1) return fail(ctx, MLM_EINVAL, "mlm_fp64_probe: bad argument");
+    DeviceGuard g(ctx->device);
+    int rc = ensure_dbuf(ctx, 256);
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream[0];
+    double h[24];
+    for (int k = 0; k < 24; ++k) h[k] = (k < 8) ? 1.0 + 0.01 * k : (k < 16 ? 0.999999 - 1e-7 * k : 1e-7 * (k - 15));
+    CK(cudaMemcpyAsync(ctx->dbuf, h, sizeof(h), cudaMemcpyHostToDevice, st));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    const int iters = 2048, blocks = ctx->sm_count * blocks_per_sm, threads = 128;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CK(cudaEventRecord(e0, st));
+        if (mode == 1) k_fp64_probe<1><<<blocks, threads, 0, st>>>((double*)ctx->dbuf + 32, iters, (const double*)ctx->dbuf);
+        else k_fp64_probe<2><<<blocks, threads, 0, st>>>((double*)ctx->dbuf + 32, iters, (const double*)ctx->dbuf);
+        CK(cudaEventRecord(e1, st));
+        CK(cudaEventSynchronize(e1));
+        ctx->launches++;
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double inst = 32.0 * (double)iters * (double)blocks * (double)threads;
+        const double r = inst / (ms * 1e-3);
+        if (rep > 0 && r > best) best = r;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    CK(cudaGetLastError());
+    *inst_per_s = best;
     return 0;
 }
 

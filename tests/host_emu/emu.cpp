@@ -83,7 +83,8 @@ extern "C" void emu_strip(double s, double q, double rho, double Gamma, const do
         const int before = hist;
         hist = advance_roots(c, T.s, z, zp, 1, hist, r.flags);
         if (before == 0 || hist < 2) ++cold;
-        accumulate_images<4>(T, sf, zeta_i, z, 1, r);
+        cd scratch[10];
+        accumulate_images<4>(T, sf, zeta_i, z, 1, scratch, 1, r);
         A0[i] = r.A0; A2[i] = r.A2; A4[i] = r.A4;
         nimg[i] = (unsigned char)r.nimg; flags[i] = (unsigned char)r.flags;
     }
