@@ -76,6 +76,11 @@ int mlm_ipc_close(mlm_context* ctx, void* p);
 
 /* rows per warm-start strip of mlm_map (default 64; env MLM_MAP_STRIP at mlm_create) */
 int mlm_map_strip(mlm_context* ctx);
+/* Set it (0 = default 64).  The strip length is a numerical parameter of the map kernel, like a tile
+ * size: a shorter strip means more independent work items (better tail behaviour of small launches,
+ * e.g. 1/8 of a map per GPU) and more cold root solves (~ +2000/L FP64 instructions per pixel).
+ * For a fixed strip length the map is bit-identical under any strip-aligned sharding. */
+int mlm_set_map_strip(mlm_context* ctx, int strip);
 
 /* ---- the fused path: replaces the per-position body of example(), multipoles.py:181-202
  *      (_solvelenseq :156-165, selection :182-183, Wk :185-201, hexadecapole :67-148) -------- */
@@ -98,6 +103,15 @@ int mlm_points_host(mlm_context* ctx, double s, double q, double rho, double Gam
 int mlm_map(mlm_context* ctx, double s, double q, double rho, double Gamma,
             double x0, double y0, double dx, double dy, int64_t nx, int64_t row0, int64_t nrows, int order,
             double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags, void* stream);
+/* Same, restricted to the strips k = kphase (mod kstep) of the row range (strip k = rows
+ * [k L, (k+1) L), L = mlm_map_strip()); rows of other strips are not touched.  Cyclic sharding of a
+ * map over GPUs: rank r of N calls it with row0 = 0, nrows = ny, kphase = r, kstep = N and output
+ * pointers to the FULL map -- every rank then gets the same mix of cheap and expensive (near-caustic)
+ * rows, and the union over ranks is bit-identical to the unsharded map. */
+int mlm_map_strips(mlm_context* ctx, double s, double q, double rho, double Gamma,
+                   double x0, double y0, double dx, double dy, int64_t nx, int64_t row0, int64_t nrows,
+                   int64_t kphase, int64_t kstep, int order,
+                   double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags, void* stream);
 int mlm_map_host(mlm_context* ctx, double s, double q, double rho, double Gamma,
                  double x0, double y0, double dx, double dy, int64_t nx, int64_t row0, int64_t nrows, int order,
                  double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags);

@@ -26,6 +26,7 @@ SIGNATURES = {
     "mlm_launch_count": [_P, ctypes.POINTER(_L)],
     "mlm_synchronize": [_P],
     "mlm_map_strip": [_P],
+    "mlm_set_map_strip": [_P, _I],
     "mlm_alloc_host": [_P, _L, ctypes.POINTER(_P)],
     "mlm_free_host": [_P, _P],
     "mlm_device_alloc": [_P, _L, ctypes.POINTER(_P)],
@@ -36,6 +37,7 @@ SIGNATURES = {
     "mlm_points": [_P, _D, _D, _D, _D, _P, _L, _I, _P, _P, _P, _P, _P, _P],
     "mlm_points_host": [_P, _D, _D, _D, _D, _P, _L, _I, _P, _P, _P, _P, _P],
     "mlm_map": [_P, _D, _D, _D, _D, _D, _D, _D, _D, _L, _L, _L, _I, _P, _P, _P, _P, _P, _P],
+    "mlm_map_strips": [_P, _D, _D, _D, _D, _D, _D, _D, _D, _L, _L, _L, _L, _L, _I, _P, _P, _P, _P, _P, _P],
     "mlm_map_host": [_P, _D, _D, _D, _D, _D, _D, _D, _D, _L, _L, _L, _I, _P, _P, _P, _P, _P],
     "mlm_models": [_P, _P, _P, _P, _P, _P, _P, _L, _D, _D, _L, _I, _P, _P, _P, _P, _P, _P],
     "mlm_models_host": [_P, _P, _P, _P, _P, _P, _P, _L, _D, _D, _L, _I, _P, _P, _P, _P, _P],
@@ -117,6 +119,13 @@ class Context:
         v = _D(0.0)
         self.check(self.lib.mlm_fp64_peak(self.handle, ctypes.byref(v)), "mlm_fp64_peak")
         return float(v.value)
+
+    def map_strip(self) -> int:
+        return int(self.lib.mlm_map_strip(self.handle))
+
+    def set_map_strip(self, strip: int):
+        """Rows per warm-start strip of the map kernel (0: default 64)."""
+        self.check(self.lib.mlm_set_map_strip(self.handle, int(strip)), "mlm_set_map_strip")
 
     def fp64_probe(self, mode: int, blocks_per_sm: int) -> float:
         v = _D(0.0)

@@ -13,7 +13,7 @@ import numpy as np
 from . import _capi
 
 __all__ = ["Magnification", "magnification_points", "magnification_map", "magnification_models",
-           "map_coordinates", "lightcurve_coordinates", "alloc_outputs", "ALL_OUTPUTS", "map_device", "points_device",
+           "map_coordinates", "lightcurve_coordinates", "alloc_outputs", "ALL_OUTPUTS", "map_device", "map_strips_device", "points_device",
            "models_device"]
 
 
@@ -142,6 +142,14 @@ def map_device(s, q, rho, Gamma, x0, y0, dx, dy, nx, row0, nrows, A0, A2, A4, ni
     ctx = _capi.context(device)
     ctx.check(ctx.lib.mlm_map(ctx.handle, s, q, rho, Gamma, x0, y0, dx, dy, nx, row0, nrows, order,
                               _p(A0), _p(A2), _p(A4), _p(nimg), _p(flags), _p(stream)), "mlm_map")
+
+
+def map_strips_device(s, q, rho, Gamma, x0, y0, dx, dy, nx, row0, nrows, kphase, kstep, A0, A2, A4, nimg=None,
+                      flags=None, order=4, stream=None, device=None):
+    """Strips k = kphase (mod kstep) of the rows [row0, row0+nrows) only (cyclic sharding over GPUs)."""
+    ctx = _capi.context(device)
+    ctx.check(ctx.lib.mlm_map_strips(ctx.handle, s, q, rho, Gamma, x0, y0, dx, dy, nx, row0, nrows, kphase, kstep,
+                                     order, _p(A0), _p(A2), _p(A4), _p(nimg), _p(flags), _p(stream)), "mlm_map_strips")
 
 
 def models_device(s, q, rho, Gamma, u0, alpha, M, tau0, dtau, T, A0, A2, A4, nimg=None, flags=None, order=4,

@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -74,7 +75,8 @@ k_points(const __grid_constant__ LensTable T, const SourceFactors sf, const doub
 template <int ORDER>
 __global__ void __launch_bounds__(MLM_BLOCK, MLM_MAP_MINBLOCKS)
 k_map(const __grid_constant__ LensTable T, const SourceFactors sf, double x0, double y0, double dx, double dy,
-      double shift, int64_t nx, int64_t row0, int64_t nrows, int strip, double* __restrict__ A0,
+      double shift, int64_t nx, int64_t row0, int64_t nrows, int strip, int64_t kphase, int64_t kstep,
+      int64_t i_first, int64_t i_count, int64_t i_axis, double* __restrict__ A0,
       double* __restrict__ A2, double* __restrict__ A4, uint8_t* __restrict__ nimg, uint8_t* __restrict__ flags) {
     // root store of this thread: current and previous roots, [k][thread] so that a warp touches
     // 512 contiguous bytes per k (conflict-free); keeps 20 doubles out of the register file
@@ -87,8 +89,19 @@ k_map(const __grid_constant__ LensTable T, const SourceFactors sf, double x0, do
     // x = x0 + (col + 0.5) dx with two roundings (no FMA), so that host code can reproduce
     // the coordinates bit for bit with the same expression.
     const double x = __dadd_rn(__dadd_rn(x0, __dmul_rn((double)col + 0.5, dx)), -shift);
-    const int64_t k_first = row0 / strip, k_last = (row0 + nrows - 1) / strip;
-    for (int64_t k = k_first + blockIdx.y; k <= k_last; k += gridDim.y) {
+    // This launch owns the strips k = kphase + i kstep, i = i_first .. i_first + i_count - 1 (kstep = 1:
+    // every strip of the row range; kstep = world, kphase = rank: cyclic sharding over GPUs, which
+    // balances the load whatever the caustic geometry).
+    // They are visited from the lens axis (y = 0, index i_axis) outwards, alternating sides: the
+    // caustics -- the 5-image, i.e. expensive, pixels -- sit on the axis, so the heavy blocks are
+    // scheduled first and the tail of the launch is made of cheap ones.  Pure scheduling order:
+    // the arithmetic of a strip does not depend on it.
+    const int64_t n_lo = i_axis, n_hi = i_count - 1 - i_axis, n_min = n_lo < n_hi ? n_lo : n_hi;
+    for (int64_t j = blockIdx.y; j < i_count; j += gridDim.y) {
+        int64_t ii;
+        if (j <= 2 * n_min) ii = (j & 1) ? i_axis + (j + 1) / 2 : i_axis - j / 2;
+        else ii = (n_hi > n_lo) ? i_axis + (j - n_min) : i_axis - (j - n_min);
+        const int64_t k = kphase + (i_first + ii) * kstep;
         const int64_t ra = (k * strip > row0) ? k * strip : row0;
         const int64_t rb = ((k + 1) * strip < row0 + nrows) ? (k + 1) * strip : row0 + nrows;
         int hist = 0;
@@ -407,6 +420,12 @@ int mlm_launch_count(mlm_context* ctx, int64_t* out) {
 
 int mlm_map_strip(mlm_context* ctx) { return ctx ? ctx->map_strip : MLM_EINVAL; }
 
+int mlm_set_map_strip(mlm_context* ctx, int strip) {
+    if (!ctx || strip < 0 || strip > 4096) return fail(ctx, MLM_EINVAL, "mlm_set_map_strip: bad argument");
+    ctx->map_strip = strip ? strip : 64;
+    return 0;
+}
+
 int mlm_synchronize(mlm_context* ctx) {
     if (!ctx) return fail(ctx, MLM_EINVAL, "mlm_synchronize: NULL context");
     DeviceGuard g(ctx->device);
@@ -499,11 +518,12 @@ int mlm_points(mlm_context* ctx, double s, double q, double rho, double Gamma, c
     return 0;
 }
 
-int mlm_map(mlm_context* ctx, double s, double q, double rho, double Gamma, double x0, double y0, double dx,
-            double dy, int64_t nx, int64_t row0, int64_t nrows, int order, double* A0, double* A2, double* A4,
-            uint8_t* nimg, uint8_t* flags, void* stream) {
+int mlm_map_strips(mlm_context* ctx, double s, double q, double rho, double Gamma, double x0, double y0, double dx,
+                   double dy, int64_t nx, int64_t row0, int64_t nrows, int64_t kphase, int64_t kstep, int order,
+                   double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags, void* stream) {
     if (!ctx) return fail(ctx, MLM_EINVAL, "mlm_map: NULL context");
-    if (nx < 0 || nrows < 0 || (order != 2 && order != 4) || bad_lens(s, q))
+    if (nx < 0 || nrows < 0 || row0 < 0 || (order != 2 && order != 4) || bad_lens(s, q) || kstep < 1 || kphase < 0 ||
+        kphase >= kstep)
         return fail(ctx, MLM_EINVAL, "mlm_map: bad argument");
     if (nx == 0 || nrows == 0) return 0;
     if (!(A0 || A2 || A4 || nimg || flags)) return fail(ctx, MLM_EINVAL, "mlm_map: NULL buffer");
@@ -513,16 +533,38 @@ int mlm_map(mlm_context* ctx, double s, double q, double rho, double Gamma, doub
     const SourceFactors sf = source_factors(rho, Gamma);
     const double shift = s * q / (1.0 + q);            // multipoles.py:178
     const int strip = ctx->map_strip;
-    const int64_t nstrips = (row0 + nrows - 1) / strip - row0 / strip + 1;
-    dim3 grid((unsigned)((nx + MLM_BLOCK - 1) / MLM_BLOCK), (unsigned)(nstrips < 65535 ? nstrips : 65535));
+    const int64_t k_first = row0 / strip, k_last = (row0 + nrows - 1) / strip;
+    // strips of this launch: k = kphase + i kstep within [k_first, k_last]
+    const int64_t kk0 = k_first + (((kphase - k_first) % kstep) + kstep) % kstep;
+    if (kk0 > k_last) return 0;
+    const int64_t i_first = (kk0 - kphase) / kstep, i_count = (k_last - kk0) / kstep + 1;
+    // strip that holds the lens axis y = 0 (row index (0 - y0)/dy - 0.5) -> nearest owned strip
+    int64_t i_axis = 0;
+    {
+        const double r_axis = (dy != 0.0) ? (-y0 / dy - 0.5) : 0.0;
+        double ia = std::floor((r_axis / (double)strip - (double)kphase) / (double)kstep + 0.5) - (double)i_first;
+        if (!(ia >= 0.0)) ia = 0.0;                                  // also catches NaN
+        if (ia > (double)(i_count - 1)) ia = (double)(i_count - 1);
+        i_axis = (int64_t)ia;
+    }
+    dim3 grid((unsigned)((nx + MLM_BLOCK - 1) / MLM_BLOCK), (unsigned)(i_count < 65535 ? i_count : 65535));
     cudaStream_t st = pick(ctx, stream);
     if (order == 4)
-        k_map<4><<<grid, MLM_BLOCK, 0, st>>>(T, sf, x0, y0, dx, dy, shift, nx, row0, nrows, strip, A0, A2, A4, nimg, flags);
+        k_map<4><<<grid, MLM_BLOCK, 0, st>>>(T, sf, x0, y0, dx, dy, shift, nx, row0, nrows, strip, kphase, kstep, i_first,
+                                              i_count, i_axis, A0, A2, A4, nimg, flags);
     else
-        k_map<2><<<grid, MLM_BLOCK, 0, st>>>(T, sf, x0, y0, dx, dy, shift, nx, row0, nrows, strip, A0, A2, A4, nimg, flags);
+        k_map<2><<<grid, MLM_BLOCK, 0, st>>>(T, sf, x0, y0, dx, dy, shift, nx, row0, nrows, strip, kphase, kstep, i_first,
+                                              i_count, i_axis, A0, A2, A4, nimg, flags);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;
+}
+
+int mlm_map(mlm_context* ctx, double s, double q, double rho, double Gamma, double x0, double y0, double dx,
+            double dy, int64_t nx, int64_t row0, int64_t nrows, int order, double* A0, double* A2, double* A4,
+            uint8_t* nimg, uint8_t* flags, void* stream) {
+    return mlm_map_strips(ctx, s, q, rho, Gamma, x0, y0, dx, dy, nx, row0, nrows, 0, 1, order, A0, A2, A4, nimg, flags,
+                          stream);
 }
 
 int mlm_models(mlm_context* ctx, const double* s, const double* q, const double* rho, const double* Gamma,

@@ -20,7 +20,7 @@ from __future__ import annotations
 
 from dataclasses import dataclass
 
-__all__ = ["shard_range", "ShardPlan", "plan_map", "full_map_layout", "BYTES_PER_POSITION", "KEYS", "ShardedMap"]
+__all__ = ["shard_range", "ShardPlan", "plan_map", "full_map_layout", "auto_strip", "BYTES_PER_POSITION", "KEYS", "ShardedMap"]
 
 BYTES_PER_POSITION = 26           # 3 x float64 + 2 x uint8
 KEYS = (("A0", 8), ("A2", 8), ("A4", 8), ("nimg", 1), ("flags", 1))     # output arrays and their item sizes
@@ -68,6 +68,15 @@ def plan_map(ny: int, rank: int, world: int, nchunks: int = 4, align: int = MAP_
     return ShardPlan(rank, world, lo, n, max_rows, tuple(chunks))
 
 
+def auto_strip(nx: int, rows_per_rank: int, resident_threads: int = 148 * 16 * 32, waves: int = 6) -> int:
+    """Strip length (power of two, 8..64) that leaves every rank about `waves` waves of work items:
+    one work item = one column of one strip; a B200 keeps 148 SMs x 16 warps of them resident."""
+    strip = 64
+    while strip > 8 and nx * max(rows_per_rank, 1) // strip < waves * resident_threads:
+        strip //= 2
+    return strip
+
+
 def full_map_layout(nx: int, ny: int) -> tuple[dict, int]:
     """Byte offsets of the five full-map SoA arrays inside rank 0's shared buffer (each 256-byte
     aligned) and the total size: {"A0": off, ...}, nbytes."""
@@ -95,10 +104,16 @@ class ShardedMap:
     """
 
     def __init__(self, nx: int, ny: int, rank: int = 0, world: int = 1, device=None, nchunks: int | None = None,
-                 group=None, align: int = MAP_STRIP, gather: str | None = None, compute_fn=None):
+                 group=None, align: int | None = None, gather: str | None = None, compute_fn=None,
+                 outputs=None, layout: str | None = None):
         import torch
         self.torch = torch
         self.nx, self.ny = nx, ny
+        # strip length of the map kernel = alignment of the shards.  None: chosen from the per-rank
+        # size (auto_strip) -- the same function of (nx, ny, world) on every rank.  For a given strip
+        # length the sharded map is bit-identical to the unsharded one (Context.set_map_strip).
+        if align is None:
+            align = auto_strip(nx, -(-ny // world)) if compute_fn is None else MAP_STRIP
         self.align = align
         self.group = group
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -108,10 +123,23 @@ class ShardedMap:
         if gather not in ("none", "p2p", "nccl"):
             raise ValueError("gather must be 'none', 'p2p' or 'nccl'")
         self.gather = gather
+        # how the strips of the map are dealt to the ranks: "block" = one contiguous, strip-aligned row
+        # block per rank; "cyclic" = strip k goes to rank k mod world (same mix of cheap and expensive
+        # rows on every rank; needs the p2p gather, where every rank addresses the full map)
+        if layout is None:
+            layout = "cyclic" if (gather == "p2p" and world > 1) else "block"
+        if layout not in ("block", "cyclic") or (layout == "cyclic" and world > 1 and gather != "p2p"):
+            raise ValueError("layout must be 'block' or 'cyclic' (cyclic needs gather='p2p')")
+        self.layout = layout
         if nchunks is None:
             nchunks = 4 if (world > 1 and gather == "nccl") else 1       # chunks only pipeline the NCCL gather
         self.plan = plan_map(ny, rank, world, nchunks, align)
         self.compute_fn = compute_fn
+        # subset of the five output arrays that is stored / gathered (None: all); the kernel takes
+        # NULL for the others
+        self.outputs = tuple(k for k, _ in KEYS) if outputs is None else tuple(outputs)
+        if not self.outputs or set(self.outputs) - {k for k, _ in KEYS}:
+            raise ValueError("outputs must be a non-empty subset of A0, A2, A4, nimg, flags")
         n_slot = self.plan.max_rows * nx
         self.n_slot = n_slot
         self.full = None
@@ -149,9 +177,10 @@ class ShardedMap:
             base = ctx.ipc_open(box[0])
         self._ipc = (ctx, base, p.rank == 0)
         n = self.nx * self.ny
-        lo = p.row0 * self.nx
-        # launch targets: raw addresses of this rank's row window inside rank 0's buffer (peer-mapped
-        # on ranks > 0, where torch never touches the memory)
+        lo = p.row0 * self.nx if self.layout == "block" else 0
+        # launch targets: raw addresses of this rank's row window (block layout) or of the whole map
+        # (cyclic layout) inside rank 0's buffer (peer-mapped on ranks > 0, where torch never touches
+        # the memory)
         self.local = {key: base + layout[key] + lo * item for key, item in KEYS}
         self.full_map = None
         if p.rank == 0:
@@ -176,16 +205,41 @@ class ShardedMap:
             ctx.device_free(base)
 
     # ---- work --------------------------------------------------------------------------------------
+    def _set_strip(self):
+        """Make the context's strip length ours; returns the previous one (restored after the launches
+        are enqueued: the strip is read on the host at launch time)."""
+        if self.compute_fn is not None:
+            return None
+        from . import _capi
+        ctx = _capi.context(self.device.index)
+        old = ctx.map_strip()
+        if old != self.align:
+            ctx.set_map_strip(self.align)
+        return old
+
+    def _restore_strip(self, old):
+        if old is not None and old != self.align:
+            from . import _capi
+            _capi.context(self.device.index).set_map_strip(old)
+
     def _launch(self, s, q, rho, Gamma, x0, y0, dx, dy, row0, nrows, views, order, stream):
         if self.compute_fn is not None:
             self.compute_fn(s, q, rho, Gamma, x0, y0, dx, dy, self.nx, row0, nrows, views, order)
             return
         from .batched import map_device
-        map_device(s, q, rho, Gamma, x0, y0, dx, dy, self.nx, row0, nrows, views["A0"], views["A2"], views["A4"],
-                   views["nimg"], views["flags"], order=order, stream=stream, device=self.device.index)
+        v = {k: (views[k] if k in self.outputs else None) for k, _ in KEYS}
+        map_device(s, q, rho, Gamma, x0, y0, dx, dy, self.nx, row0, nrows, v["A0"], v["A2"], v["A4"],
+                   v["nimg"], v["flags"], order=order, stream=stream, device=self.device.index)
 
     def compute(self, s, q, rho, Gamma, x0, y0, dx, dy, order=4, gather=True):
         """Enqueue this rank's shard (and the gather to rank 0 when world > 1)."""
+        old = self._set_strip()
+        try:
+            self._compute(s, q, rho, Gamma, x0, y0, dx, dy, order, gather)
+        finally:
+            self._restore_strip(old)
+
+    def _compute(self, s, q, rho, Gamma, x0, y0, dx, dy, order, gather):
         import torch.distributed as dist
         t = self.torch
         p, nx = self.plan, self.nx
@@ -193,7 +247,13 @@ class ShardedMap:
         stream = cur.cuda_stream if cur is not None else None
         if self.gather == "p2p" and p.world > 1:
             # one launch; the kernel's stores ARE the gather (peer memory on ranks > 0)
-            if p.nrows:
+            if self.layout == "cyclic":
+                from .batched import map_strips_device
+                v = {k: (self.local[k] if k in self.outputs else None) for k, _ in KEYS}
+                map_strips_device(s, q, rho, Gamma, x0, y0, dx, dy, nx, 0, self.ny, p.rank, p.world, v["A0"], v["A2"],
+                                  v["A4"], v["nimg"], v["flags"], order=order, stream=stream,
+                                  device=self.device.index)
+            elif p.nrows:
                 self._launch(s, q, rho, Gamma, x0, y0, dx, dy, p.row0, p.nrows, self.local, order, stream)
             if gather:
                 dist.all_reduce(self._fence, group=self.group)      # stream-ordered completion fence
@@ -212,7 +272,7 @@ class ShardedMap:
                 if self.comm_stream is not None:
                     self.comm_stream.wait_stream(cur)
                 with (t.cuda.stream(self.comm_stream) if self.comm_stream is not None else _null()):
-                    for key, _ in KEYS:
+                    for key in self.outputs:
                         src = buf[key][o:o + cnt]
                         dst = [self.full[r][key][o:o + cnt] for r in range(p.world)] if p.rank == 0 else None
                         dist.gather(src, dst, dst=0, group=self.group)

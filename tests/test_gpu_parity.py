@@ -253,6 +253,17 @@ def test_row_sharding_is_bitwise_identical(mb):
             parts.append(mb.magnification_map(s, q, rho, G, x0, y0, dx, dy, nx, ny, row0=lo, nrows=hi - lo))
         for k in ("A0", "A2", "A4", "nimg", "flags"):
             assert np.array_equal(np.concatenate([p[k] for p in parts], 0), full[k]), (world, k)
+    # cyclic sharding: strips k = r (mod world) written by "rank" r into the same full-map buffers
+    import torch
+    from microlensing_b200.batched import map_strips_device
+    for world in (2, 3):
+        bufs = [torch.full((ny * nx,), -1.0, dtype=torch.float64, device="cuda") for _ in range(3)] + \
+               [torch.full((ny * nx,), 255, dtype=torch.uint8, device="cuda") for _ in range(2)]
+        for r in range(world):
+            map_strips_device(s, q, rho, G, x0, y0, dx, dy, nx, 0, ny, r, world, *bufs)
+        torch.cuda.synchronize()
+        for k, b in zip(("A0", "A2", "A4", "nimg", "flags"), bufs):
+            assert np.array_equal(b.cpu().numpy().reshape(ny, nx), full[k]), (world, k)
     # unaligned shards still agree to rounding (a strip cut in two starts with one more cold solve)
     a = mb.magnification_map(s, q, rho, G, x0, y0, dx, dy, nx, ny, row0=0, nrows=50)
     b = mb.magnification_map(s, q, rho, G, x0, y0, dx, dy, nx, ny, row0=50, nrows=ny - 50)
@@ -266,13 +277,23 @@ def test_device_pointer_api_and_sharded_map(mb):
     s, q, rho, G = 0.8, 0.1, 1e-3, 0.5
     nx = ny = 192
     x0, y0, dx, dy = 0.11 - 0.75, -0.75, 1.5 / nx, 1.5 / ny
-    sm = ShardedMap(nx, ny, 0, 1, nchunks=3)
+    strip = mb._capi.context().map_strip()
+    sm = ShardedMap(nx, ny, 0, 1, nchunks=3, align=strip)
     sm.compute(s, q, rho, G, x0, y0, dx, dy)
     torch.cuda.synchronize()
     dev = sm.assemble_host()
     host = mb.magnification_map(s, q, rho, G, x0, y0, dx, dy, nx, ny)
     for k in ("A0", "A2", "A4", "nimg", "flags"):
         assert np.array_equal(dev[k], host[k]), k
+    # output subset: unselected arrays are never written
+    sm2 = ShardedMap(nx, ny, 0, 1, outputs=("A4", "flags"), align=strip)
+    for k in ("A0", "A2", "nimg"):
+        sm2.local[k].fill_(7)
+    sm2.compute(s, q, rho, G, x0, y0, dx, dy)
+    torch.cuda.synchronize()
+    d2 = sm2.assemble_host()
+    assert np.array_equal(d2["A4"], host["A4"]) and np.array_equal(d2["flags"], host["flags"])
+    assert (d2["A0"] == 7).all() and (d2["nimg"] == 7).all()
 
 
 def test_output_selection(mb):
@@ -292,7 +313,7 @@ def test_output_selection(mb):
         mb.magnification_map(s, q, rho, G, x0, y0, dx, dy, nx, ny, outputs=())
 
 
-def _two_gpu_worker(rank, world, port, gather, out_dir):
+def _two_gpu_worker(rank, world, port, gather, layout, out_dir):
     import torch
     import torch.distributed as dist
     os.environ["MLM_DEVICE"] = str(rank)
@@ -304,21 +325,21 @@ def _two_gpu_worker(rank, world, port, gather, out_dir):
         s, q, rho, G = 1.0, 0.5, 1e-3, 0.5
         nx, ny = 512, 320
         x0, y0, dx, dy = -0.88, -0.8, 1.6 / nx, 1.6 / ny
-        sm = ShardedMap(nx, ny, rank, world, gather=gather)
+        sm = ShardedMap(nx, ny, rank, world, gather=gather, layout=layout)
         for _ in range(2):
             sm.compute(s, q, rho, G, x0, y0, dx, dy)
         torch.cuda.synchronize()
         full = sm.assemble_host()
         if rank == 0:
-            np.savez(os.path.join(out_dir, f"full_{gather}.npz"), **full)
+            np.savez(os.path.join(out_dir, f"full_{gather}_{layout}.npz"), **full)
         dist.barrier()
         sm.close()
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("gather", ["p2p", "nccl"])
-def test_two_gpu_sharded_map_equals_single_gpu(mb, tmp_path, gather):
+@pytest.mark.parametrize("gather,layout", [("p2p", "cyclic"), ("p2p", "block"), ("nccl", "block")])
+def test_two_gpu_sharded_map_equals_single_gpu(mb, tmp_path, gather, layout):
     """Row-sharded over 2 GPUs with the fused peer-store gather (and the NCCL gather): rank 0's
     assembled map is bit-identical to the single-GPU map."""
     import torch
@@ -329,13 +350,26 @@ def test_two_gpu_sharded_map_equals_single_gpu(mb, tmp_path, gather):
     with socket.socket() as sk:
         sk.bind(("127.0.0.1", 0))
         port = sk.getsockname()[1]
-    mp.spawn(_two_gpu_worker, args=(2, port, gather, str(tmp_path)), nprocs=2, join=True)
-    got = np.load(tmp_path / f"full_{gather}.npz")
+    mp.spawn(_two_gpu_worker, args=(2, port, gather, layout, str(tmp_path)), nprocs=2, join=True)
+    got = np.load(tmp_path / f"full_{gather}_{layout}.npz")
     s, q, rho, G = 1.0, 0.5, 1e-3, 0.5
     nx, ny = 512, 320
-    one = mb.magnification_map(s, q, rho, G, -0.88, -0.8, 1.6 / nx, 1.6 / ny, nx, ny)
+    # the single-GPU map with the strip length the sharded run picked (auto_strip) is bit-identical;
+    # with the default strip it agrees to rounding
+    from microlensing_b200.sharding import auto_strip
+    ctx = mb._capi.context()
+    default = mb.magnification_map(s, q, rho, G, -0.88, -0.8, 1.6 / nx, 1.6 / ny, nx, ny)
+    old = ctx.map_strip()
+    ctx.set_map_strip(auto_strip(nx, ny // 2))
+    try:
+        one = mb.magnification_map(s, q, rho, G, -0.88, -0.8, 1.6 / nx, 1.6 / ny, nx, ny)
+    finally:
+        ctx.set_map_strip(old)
     for k in ("A0", "A2", "A4", "nimg", "flags"):
         assert np.array_equal(got[k], one[k]), k
+    assert np.array_equal(got["nimg"], default["nimg"])
+    ok = (default["flags"] == 0) & (got["flags"] == 0)
+    assert np.abs(got["A4"] / default["A4"] - 1)[ok].max() < 1e-9
 
 
 def test_full_size_properties(mb):
