@@ -126,6 +126,19 @@ int mlm_models_host(mlm_context* ctx, const double* s, const double* q, const do
                     const double* u0, const double* alpha, int64_t M, double tau0, double dtau, int64_t T, int order,
                     double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags);
 
+/* Model grid with the light-curve fit fused in ("fused chi^2 reduction against observed
+ * fluxes"): same models and epochs as mlm_models, but instead of M x T magnifications the kernel returns,
+ * per model, the least-squares linear flux fit F_t = Fs A_t + Fb of the model magnifications A_t (A4 for
+ * order 4, A2 for order 2) to the observed fluxes flux[T] with weights weight[T] = 1/sigma^2:
+ *   stats[8 m + 0..7] = { chi2_min, Fs, Fb, sum w A, sum w A^2, sum w A f, #epochs with 5 images, #flagged epochs }
+ * (per-block fixed-order reduction: deterministic). */
+int mlm_models_chi2(mlm_context* ctx, const double* s, const double* q, const double* rho, const double* Gamma,
+                    const double* u0, const double* alpha, int64_t M, double tau0, double dtau, int64_t T, int order,
+                    const double* flux, const double* weight, double* stats, void* stream);
+int mlm_models_chi2_host(mlm_context* ctx, const double* s, const double* q, const double* rho, const double* Gamma,
+                         const double* u0, const double* alpha, int64_t M, double tau0, double dtau, int64_t T, int order,
+                         const double* flux, const double* weight, double* stats);
+
 /* ---- drop-ins for the individual reference functions ------------------------------------ */
 
 /* quadrupole(Wk,rho,Gamma) multipoles.py:12 (order 2, out = [A0,A2]) and

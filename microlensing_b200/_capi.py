@@ -41,6 +41,8 @@ SIGNATURES = {
     "mlm_map_host": [_P, _D, _D, _D, _D, _D, _D, _D, _D, _L, _L, _L, _I, _P, _P, _P, _P, _P],
     "mlm_models": [_P, _P, _P, _P, _P, _P, _P, _L, _D, _D, _L, _I, _P, _P, _P, _P, _P, _P],
     "mlm_models_host": [_P, _P, _P, _P, _P, _P, _P, _L, _D, _D, _L, _I, _P, _P, _P, _P, _P],
+    "mlm_models_chi2": [_P, _P, _P, _P, _P, _P, _P, _L, _D, _D, _L, _I, _P, _P, _P, _P],
+    "mlm_models_chi2_host": [_P, _P, _P, _P, _P, _P, _P, _L, _D, _D, _L, _I, _P, _P, _P],
     "mlm_from_wk": [_P, _P, _L, _I, _D, _D, _P, _P],
     "mlm_from_wk_host": [_P, _P, _L, _I, _D, _D, _P],
     "mlm_solve": [_P, _D, _D, _P, _L, _P, _P],

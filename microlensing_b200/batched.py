@@ -12,7 +12,8 @@ import numpy as np
 
 from . import _capi
 
-__all__ = ["Magnification", "magnification_points", "magnification_map", "magnification_models",
+__all__ = ["Magnification", "magnification_points", "magnification_map", "magnification_models", "models_chi2",
+           "models_chi2_device",
            "map_coordinates", "lightcurve_coordinates", "alloc_outputs", "ALL_OUTPUTS", "map_device", "map_strips_device", "points_device",
            "models_device"]
 
@@ -126,6 +127,29 @@ def magnification_models(s, q, rho, Gamma, u0, alpha, tau0, dtau, T, order=4, ou
     return out
 
 
+def models_chi2(s, q, rho, Gamma, u0, alpha, tau0, dtau, flux, sigma, order=4, device=None) -> dict:
+    """Fit statistics of a grid of M models against ONE observed light curve: the model
+    magnifications never leave the GPU.  `flux`, `sigma`: observed fluxes and their errors at the epochs
+    tau_t = tau0 + t dtau.  Returns arrays of length M: chi2 (minimised over the source and blend fluxes Fs, Fb
+    of F = Fs A + Fb), Fs, Fb, the sums SA, SAA, SAF, and the counts n5 (5-image epochs), nflag."""
+    ctx = _capi.context(device)
+    arrs = [np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float64), np.shape(s)))
+            for a in (s, q, rho, Gamma, u0, alpha)]
+    M = arrs[0].size
+    if not (np.all(arrs[0] > 0) and np.all(arrs[1] > 0)):
+        raise ValueError("models_chi2: s and q must be positive")
+    flux = np.ascontiguousarray(flux, dtype=np.float64).ravel()
+    sigma = np.ascontiguousarray(np.broadcast_to(np.asarray(sigma, dtype=np.float64), flux.shape))
+    if not np.all(sigma > 0):
+        raise ValueError("models_chi2: sigma must be positive")
+    w = 1.0 / (sigma * sigma)
+    stats = np.empty((M, 8), dtype=np.float64)
+    ctx.check(ctx.lib.mlm_models_chi2_host(ctx.handle, *[_capi.ptr(a) for a in arrs], M, tau0, dtau, flux.size, order,
+                                           _capi.ptr(flux), _capi.ptr(w), _capi.ptr(stats)), "mlm_models_chi2_host")
+    keys = ("chi2", "Fs", "Fb", "SA", "SAA", "SAF", "n5", "nflag")
+    return Magnification({k: stats[:, i].copy() for i, k in enumerate(keys)})
+
+
 # ---- device-pointer variants (enqueue only; buffers e.g. torch CUDA tensors) -----------------
 def _p(x):
     return _capi.ptr(x)
@@ -150,6 +174,13 @@ def map_strips_device(s, q, rho, Gamma, x0, y0, dx, dy, nx, row0, nrows, kphase,
     ctx = _capi.context(device)
     ctx.check(ctx.lib.mlm_map_strips(ctx.handle, s, q, rho, Gamma, x0, y0, dx, dy, nx, row0, nrows, kphase, kstep,
                                      order, _p(A0), _p(A2), _p(A4), _p(nimg), _p(flags), _p(stream)), "mlm_map_strips")
+
+
+def models_chi2_device(s, q, rho, Gamma, u0, alpha, M, tau0, dtau, T, flux, weight, stats, order=4, stream=None,
+                       device=None):
+    ctx = _capi.context(device)
+    ctx.check(ctx.lib.mlm_models_chi2(ctx.handle, _p(s), _p(q), _p(rho), _p(Gamma), _p(u0), _p(alpha), M, tau0, dtau, T,
+                                      order, _p(flux), _p(weight), _p(stats), _p(stream)), "mlm_models_chi2")
 
 
 def models_device(s, q, rho, Gamma, u0, alpha, M, tau0, dtau, T, A0, A2, A4, nimg=None, flags=None, order=4,

@@ -179,6 +179,91 @@ k_models(const double* __restrict__ s, const double* __restrict__ q, const doubl
     }
 }
 
+// K1d: model grid with the light-curve fit fused in.  One block = one model: the
+// threads walk their segments of the model light curve exactly like k_models, but instead of storing
+// the magnifications they accumulate the weighted sums of the linear flux fit F_t = Fs A_t + Fb
+// against observed fluxes f_t with weights w_t = 1/sigma_t^2; a fixed-order block reduction makes
+// the result deterministic.  Output per model (8 doubles):
+//   chi2 (minimised over Fs, Fb), Fs, Fb, sum w A, sum w A^2, sum w A f, #epochs with 5 images, #flagged epochs
+template <int ORDER>
+__global__ void __launch_bounds__(MLM_MODELS_BLOCK, 6)
+k_models_chi2(const double* __restrict__ s, const double* __restrict__ q, const double* __restrict__ rho,
+              const double* __restrict__ Gamma, const double* __restrict__ u0, const double* __restrict__ alpha,
+              int64_t M, double tau0, double dtau, int64_t Tn, int seg, const double* __restrict__ flux,
+              const double* __restrict__ weight, double* __restrict__ stats) {
+    __shared__ LensTable T;
+    __shared__ SourceFactors sf;
+    __shared__ double rot[3];
+    __shared__ cd s_roots[2][5][MLM_MODELS_BLOCK];
+    __shared__ cd s_rcp[10][MLM_MODELS_BLOCK];
+    __shared__ double s_red[8][MLM_MODELS_BLOCK];
+    cd* const sz = &s_roots[0][0][threadIdx.x];
+    cd* const szp = &s_roots[1][0][threadIdx.x];
+    const int64_t nseg = (Tn + seg - 1) / seg;
+    for (int64_t m = blockIdx.x; m < M; m += gridDim.x) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const double sm = s[m], qm = q[m];
+            make_table(sm, qm, &T);
+            sf = source_factors(rho[m], Gamma[m]);
+            double sa, ca;
+            sincos(alpha[m], &sa, &ca);
+            rot[0] = ca; rot[1] = sa; rot[2] = sm * qm / (1.0 + qm);
+        }
+        __syncthreads();
+        const double u = u0[m];
+        const double ur1 = __dmul_rn(u, rot[1]), ur0 = __dmul_rn(u, rot[0]);
+        double a_w = 0.0, a_wa = 0.0, a_waa = 0.0, a_wf = 0.0, a_waf = 0.0, a_wff = 0.0, a_n5 = 0.0, a_nf = 0.0;
+        for (int64_t sg = threadIdx.x; sg < nseg; sg += MLM_MODELS_BLOCK) {
+            const int64_t t0 = sg * seg;
+            const int64_t t1 = (t0 + seg < Tn) ? t0 + seg : Tn;
+            int hist = 0;
+            for (int64_t t = t0; t < t1; ++t) {
+                asm volatile("" ::: "memory");
+                const double tau = __dadd_rn(tau0, __dmul_rn((double)t, dtau));
+                const double zx = __dadd_rn(__dadd_rn(__dmul_rn(tau, rot[0]), -ur1), -rot[2]);
+                const double zy = __dadd_rn(__dmul_rn(tau, rot[1]), ur0);
+                const cd zeta = mk(zx, zy);
+                cd c[6];
+                PointResult res;
+                res.flags = 0;
+                lens_polynomial(T, zeta, c);
+                hist = advance_roots(c, T.s, sz, szp, MLM_MODELS_BLOCK, hist, res.flags);
+                accumulate_images<ORDER>(T, sf, zeta, sz, MLM_MODELS_BLOCK, &s_rcp[0][threadIdx.x], MLM_MODELS_BLOCK, res);
+                const double A = (ORDER >= 4) ? res.A4 : res.A2;
+                const double w = __ldg(weight + t), f = __ldg(flux + t);
+                const double wa = w * A;
+                a_w += w; a_wa += wa; a_waa = fma(wa, A, a_waa);
+                a_wf = fma(w, f, a_wf); a_waf = fma(wa, f, a_waf); a_wff = fma(w * f, f, a_wff);
+                a_n5 += (res.nimg == 5) ? 1.0 : 0.0;
+                a_nf += (res.flags != 0) ? 1.0 : 0.0;
+            }
+        }
+        // fixed-order tree reduction over the block
+        s_red[0][threadIdx.x] = a_w;  s_red[1][threadIdx.x] = a_wa;  s_red[2][threadIdx.x] = a_waa;
+        s_red[3][threadIdx.x] = a_wf; s_red[4][threadIdx.x] = a_waf; s_red[5][threadIdx.x] = a_wff;
+        s_red[6][threadIdx.x] = a_n5; s_red[7][threadIdx.x] = a_nf;
+        __syncthreads();
+        for (int o = MLM_MODELS_BLOCK / 2; o > 0; o >>= 1) {
+            if (threadIdx.x < o) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) s_red[k][threadIdx.x] += s_red[k][threadIdx.x + o];
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            const double S = s_red[0][0], SA = s_red[1][0], SAA = s_red[2][0], SF = s_red[3][0], SAF = s_red[4][0],
+                         SFF = s_red[5][0];
+            const double det = S * SAA - SA * SA;
+            const double Fs = (S * SAF - SA * SF) / det;
+            const double Fb = (SAA * SF - SA * SAF) / det;
+            double* o = stats + 8 * m;
+            o[0] = SFF - Fs * SAF - Fb * SF;
+            o[1] = Fs; o[2] = Fb; o[3] = SA; o[4] = SAA; o[5] = SAF; o[6] = s_red[6][0]; o[7] = s_red[7][0];
+        }
+    }
+}
+
 // K3: roots only (drop-in for _solvelenseq)
 __global__ void __launch_bounds__(MLM_BLOCK)
 k_solve(const __grid_constant__ LensTable T, const double2* __restrict__ zeta, int64_t n, double2* __restrict__ roots) {
@@ -567,6 +652,8 @@ int mlm_map(mlm_context* ctx, double s, double q, double rho, double Gamma, doub
                           stream);
 }
 
+static int models_segment(mlm_context* ctx, int64_t Tn);
+
 int mlm_models(mlm_context* ctx, const double* s, const double* q, const double* rho, const double* Gamma,
                const double* u0, const double* alpha, int64_t M, double tau0, double dtau, int64_t Tn, int order,
                double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags, void* stream) {
@@ -576,9 +663,7 @@ int mlm_models(mlm_context* ctx, const double* s, const double* q, const double*
     if (!s || !q || !rho || !Gamma || !u0 || !alpha || !(A0 || A2 || A4 || nimg || flags))
         return fail(ctx, MLM_EINVAL, "mlm_models: NULL buffer");
     DeviceGuard g(ctx->device);
-    // epochs per warm-start segment: a function of Tn only (see k_models)
-    int seg = ctx->models_segment > 0 ? ctx->models_segment : (int)((Tn + MLM_MODELS_BLOCK - 1) / MLM_MODELS_BLOCK);
-    if (ctx->models_segment <= 0) seg = seg < 4 ? 4 : (seg > 32 ? 32 : seg);
+    const int seg = models_segment(ctx, Tn);
     const int64_t nseg = (Tn + seg - 1) / seg;
     int64_t bx = (nseg + MLM_MODELS_BLOCK - 1) / MLM_MODELS_BLOCK;
     if (bx > 4096) bx = 4096;
@@ -590,6 +675,65 @@ int mlm_models(mlm_context* ctx, const double* s, const double* q, const double*
         k_models<2><<<grid, MLM_MODELS_BLOCK, 0, st>>>(s, q, rho, Gamma, u0, alpha, M, tau0, dtau, Tn, seg, A0, A2, A4, nimg, flags);
     ctx->launches++;
     CK(cudaGetLastError());
+    return 0;
+}
+
+static int models_segment(mlm_context* ctx, int64_t Tn) {
+    // epochs per warm-start segment: a function of Tn only (see k_models)
+    int seg = ctx->models_segment > 0 ? ctx->models_segment : (int)((Tn + MLM_MODELS_BLOCK - 1) / MLM_MODELS_BLOCK);
+    if (ctx->models_segment <= 0) seg = seg < 4 ? 4 : (seg > 32 ? 32 : seg);
+    return seg;
+}
+
+int mlm_models_chi2(mlm_context* ctx, const double* s, const double* q, const double* rho, const double* Gamma,
+                    const double* u0, const double* alpha, int64_t M, double tau0, double dtau, int64_t Tn, int order,
+                    const double* flux, const double* weight, double* stats, void* stream) {
+    if (!ctx) return fail(ctx, MLM_EINVAL, "mlm_models_chi2: NULL context");
+    if (M < 0 || Tn < 0 || (order != 2 && order != 4)) return fail(ctx, MLM_EINVAL, "mlm_models_chi2: bad argument");
+    if (M == 0) return 0;
+    if (!s || !q || !rho || !Gamma || !u0 || !alpha || !stats || (Tn > 0 && (!flux || !weight)))
+        return fail(ctx, MLM_EINVAL, "mlm_models_chi2: NULL buffer");
+    DeviceGuard g(ctx->device);
+    const int seg = models_segment(ctx, Tn);
+    const unsigned blocks = (unsigned)(M < 1048576 ? M : 1048576);
+    cudaStream_t st = pick(ctx, stream);
+    if (order == 4)
+        k_models_chi2<4><<<blocks, MLM_MODELS_BLOCK, 0, st>>>(s, q, rho, Gamma, u0, alpha, M, tau0, dtau, Tn, seg, flux, weight, stats);
+    else
+        k_models_chi2<2><<<blocks, MLM_MODELS_BLOCK, 0, st>>>(s, q, rho, Gamma, u0, alpha, M, tau0, dtau, Tn, seg, flux, weight, stats);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int mlm_models_chi2_host(mlm_context* ctx, const double* s, const double* q, const double* rho, const double* Gamma,
+                         const double* u0, const double* alpha, int64_t M, double tau0, double dtau, int64_t Tn,
+                         int order, const double* flux, const double* weight, double* stats) {
+    if (!ctx) return fail(ctx, MLM_EINVAL, "mlm_models_chi2_host: NULL context");
+    if (M < 0 || Tn < 0 || (order != 2 && order != 4)) return fail(ctx, MLM_EINVAL, "mlm_models_chi2_host: bad argument");
+    if (M == 0) return 0;
+    if (!s || !q || !rho || !Gamma || !u0 || !alpha || !stats || (Tn > 0 && (!flux || !weight)))
+        return fail(ctx, MLM_EINVAL, "mlm_models_chi2_host: NULL buffer");
+    DeviceGuard g(ctx->device);
+    const size_t mpad = ((size_t)M + 31) & ~(size_t)31, tpad = ((size_t)Tn + 31) & ~(size_t)31;
+    int rc = ensure_dbuf(ctx, (mpad * 14 + tpad * 2) * sizeof(double));
+    if (rc) return rc;
+    double* par = (double*)ctx->dbuf;
+    double* dflux = par + 6 * mpad;
+    double* dw = dflux + tpad;
+    double* dstats = dw + tpad;
+    const double* hp[6] = {s, q, rho, Gamma, u0, alpha};
+    cudaStream_t st = ctx->stream[0];
+    for (int i = 0; i < 6; ++i) CK(cudaMemcpyAsync(par + i * mpad, hp[i], M * 8, cudaMemcpyHostToDevice, st));
+    if (Tn > 0) {
+        CK(cudaMemcpyAsync(dflux, flux, Tn * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(dw, weight, Tn * 8, cudaMemcpyHostToDevice, st));
+    }
+    rc = mlm_models_chi2(ctx, par, par + mpad, par + 2 * mpad, par + 3 * mpad, par + 4 * mpad, par + 5 * mpad, M, tau0,
+                         dtau, Tn, order, dflux, dw, dstats, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(stats, dstats, (size_t)M * 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     return 0;
 }
 
@@ -731,11 +875,20 @@ int mlm_map_host(mlm_context* ctx, double s, double q, double rho, double Gamma,
     Scratch sc;
     int rc = carve(ctx, n, false, &sc);
     if (rc) return rc;
+    // pipelining unit: at least MLM_CHUNK_POINTS pixels, at most ~8 chunks per call (small launches
+    // leave SMs idle at the tail), a whole number of strips so that chunking does not change a bit
     int64_t rows_per = MLM_CHUNK_POINTS / nx;
+    if (rows_per < (nrows + 7) / 8) rows_per = (nrows + 7) / 8;
     if (rows_per < 1) rows_per = 1;
+    const int64_t L = ctx->map_strip;
+    rows_per = (rows_per + L - 1) / L * L;
+    // the first chunk also takes the partial strip up to the next strip boundary of the absolute row
+    // numbering, so that every later chunk starts on one
+    const int64_t first = (row0 % L) ? L - row0 % L : 0;
     int k = 0;
-    for (int64_t r = 0; r < nrows; r += rows_per, ++k) {
-        const int64_t nr = (nrows - r < rows_per) ? (nrows - r) : rows_per;
+    for (int64_t r = 0; r < nrows; ++k) {
+        int64_t nr = (k == 0 && first) ? first + rows_per : rows_per;
+        if (nr > nrows - r) nr = nrows - r;
         const int64_t off = r * nx, cnt = nr * nx;
         cudaStream_t st = ctx->stream[k & 1];
         rc = mlm_map(ctx, s, q, rho, Gamma, x0, y0, dx, dy, nx, row0 + r, nr, order, A0 ? sc.A0 + off : nullptr,
@@ -744,6 +897,7 @@ int mlm_map_host(mlm_context* ctx, double s, double q, double rho, double Gamma,
         if (rc) return rc;
         rc = d2h_chunk(ctx, sc, off, cnt, A0, A2, A4, nimg, flags, st);
         if (rc) return rc;
+        r += nr;
     }
     CK(cudaStreamSynchronize(ctx->stream[0]));
     CK(cudaStreamSynchronize(ctx->stream[1]));

@@ -209,6 +209,50 @@ def test_models_C5_sample_vs_oracle(mb):
     print("C5 parity:", rep)
 
 
+def test_models_chi2_fused_fit(mb):
+    """the fused chi^2 kernel equals the unfused path (light curves from
+    magnification_models, sums in NumPy) and, for one model, the oracle's light curve."""
+    from oracle import cassan_oracle as oracle
+    rng = np.random.default_rng(99)
+    M, T = 20, 700
+    s = np.exp(rng.uniform(np.log(0.6), np.log(1.6), M))
+    q = np.exp(rng.uniform(np.log(1e-3), np.log(1.), M))
+    rho = np.exp(rng.uniform(np.log(1e-4), np.log(1e-2), M))
+    G = np.full(M, 0.5)
+    u0, al = rng.uniform(-.4, .4, M), rng.uniform(0, 2 * np.pi, M)
+    tau0, dtau = -2.0, 4.0 / T
+    lc = mb.magnification_models(s, q, rho, G, u0, al, tau0, dtau, T)
+    sigma = 0.01 + 0.002 * rng.random(T)
+    flux = 3.0 * lc["A4"][0] + 0.7 + sigma * rng.normal(size=T)        # model 0 is the truth: Fs = 3, Fb = 0.7
+    r = mb.models_chi2(s, q, rho, G, u0, al, tau0, dtau, flux, sigma)
+    w = 1.0 / sigma ** 2
+
+    def fit(A):
+        S, SA, SAA, SF, SAF, SFF = w.sum(), (w * A).sum(), (w * A * A).sum(), (w * flux).sum(), (w * A * flux).sum(), (w * flux * flux).sum()
+        det = S * SAA - SA * SA
+        Fs, Fb = (S * SAF - SA * SF) / det, (SAA * SF - SA * SAF) / det
+        return ((w * (flux - Fs * A - Fb) ** 2).sum(), Fs, Fb, SA, SAA, SAF)
+
+    for m in range(M):
+        chi2, Fs, Fb, SA, SAA, SAF = fit(lc["A4"][m])
+        assert np.allclose([r["Fs"][m], r["Fb"][m], r["SA"][m], r["SAA"][m], r["SAF"][m]], [Fs, Fb, SA, SAA, SAF],
+                           rtol=1e-10), m
+        assert abs(r["chi2"][m] - chi2) <= 1e-7 * max(chi2, 1.0), (m, r["chi2"][m], chi2)   # chi2 = SFF - Fs SAF - Fb SF cancels
+        assert r["n5"][m] == (lc["nimg"][m] == 5).sum() and r["nflag"][m] == (lc["flags"][m] != 0).sum()
+    assert abs(r["Fs"][0] - 3.0) < 0.01 and abs(r["Fb"][0] - 0.7) < 0.02
+    assert r["chi2"][0] == r["chi2"].min() and 0.8 * T < r["chi2"][0] < 1.2 * T
+    # one model against the oracle's light curve (reference formulae)
+    m = 1
+    zeta = mb.lightcurve_coordinates(s[m], q[m], u0[m], al[m], tau0, dtau, T)
+    nb, B0, B2, B4 = oracle.batch_a4(s[m], q[m], rho[m], G[m], zeta)[:4]
+    chi2, Fs, Fb = fit(B4)[:3]
+    assert np.allclose([r["Fs"][m], r["Fb"][m]], [Fs, Fb], rtol=1e-7)
+    assert abs(r["chi2"][m] - chi2) <= 1e-6 * chi2
+    # order 2 uses the quadrupole light curve
+    r2 = mb.models_chi2(s, q, rho, G, u0, al, tau0, dtau, flux, sigma, order=2)
+    assert np.allclose(r2["SA"], (w[None, :] * lc["A2"]).sum(axis=1), rtol=1e-10)
+
+
 def test_edge_cases(mb, golden_points):
     s, q, rho, G = 1.0, 0.5, 1e-3, 0.5
     z = np.array([0j, -1 + 0j, 1e-9 + 0j, 1e-6 + 1e-6j, -1 + 1e-8j, 50 + 20j])
@@ -294,6 +338,26 @@ def test_device_pointer_api_and_sharded_map(mb):
     d2 = sm2.assemble_host()
     assert np.array_equal(d2["A4"], host["A4"]) and np.array_equal(d2["flags"], host["flags"])
     assert (d2["A0"] == 7).all() and (d2["nimg"] == 7).all()
+
+
+def test_host_chunking_is_bitwise_neutral(mb):
+    """The host entry point pipelines a large map in row chunks (kernel k+1 overlaps D2H k); the chunks
+    are whole strips, so the result equals the single-launch device API bit for bit -- also for an
+    odd width and a row range that starts inside a strip."""
+    import torch
+    from microlensing_b200.batched import map_device
+    s, q, rho, G = 0.8, 0.1, 1e-3, 0.5
+    nx, ny, row0 = 1000, 4300, 37
+    x0, y0, dx, dy = 0.11 - 0.75, -0.75, 1.5 / nx, 1.5 / ny
+    nrows = ny - row0
+    host = mb.magnification_map(s, q, rho, G, x0, y0, dx, dy, nx, ny, row0=row0, nrows=nrows)
+    n = nrows * nx
+    bufs = [torch.empty(n, dtype=torch.float64, device="cuda") for _ in range(3)] + \
+           [torch.empty(n, dtype=torch.uint8, device="cuda") for _ in range(2)]
+    map_device(s, q, rho, G, x0, y0, dx, dy, nx, row0, nrows, *bufs)
+    torch.cuda.synchronize()
+    for k, b in zip(("A0", "A2", "A4", "nimg", "flags"), bufs):
+        assert np.array_equal(b.cpu().numpy().reshape(nrows, nx), host[k]), k
 
 
 def test_output_selection(mb):
