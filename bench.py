@@ -523,6 +523,21 @@ def other_configs(mb, dev, reps=3):
           {"kernel": "k_models<4>", "f5": None})
     out["C5_models_1e4x2000"]["f5"] = float((b[3] == 5).float().mean())
     out["C5_models_1e4x2000"]["noconv_flags"] = int((b[4] & 1).sum())
+    # the same grid with the light-curve fit fused in: 8 doubles per model leave the GPU
+    from microlensing_b200.batched import models_chi2_device
+    flux_h = 2.0 * b[2][:T].cpu().numpy() + 0.5
+    sig = np.full(T, 0.01)
+    flux_d, w_d = torch.from_numpy(flux_h).to(dev), torch.from_numpy(1.0 / sig ** 2).to(dev)
+    stats = torch.empty(M * 8, dtype=torch.float64, device=dev)
+    timed(lambda: models_chi2_device(*par, M, -2.0, 4.0 / T, T, flux_d, w_d, stats, stream=st), M * T,
+          "C5_models_1e4x2000_chi2", {"kernel": "k_models_chi2<4> (fit fused: 8 doubles per model out)"})
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        r = mb.models_chi2(sv, qv, rv, gv, uv, av, -2.0, 4.0 / T, flux_h, sig)
+    dt = (time.perf_counter() - t0) / reps
+    out["C5_models_1e4x2000_chi2"]["e2e_host_api"] = {"ms": dt * 1e3, "mags_per_s": M * T / dt,
+                                                      "h2d_bytes": int(8 * (6 * M + 2 * T)), "d2h_bytes": int(64 * M),
+                                                      "best_model": int(np.argmin(r["chi2"]))}
     return out
 
 
