@@ -230,7 +230,9 @@ MLM_HD bool newton_stop(double dz2, double prev4, cd z, double s) {   // prev4 =
     const double yy = z.y * z.y;
     const double z2 = fma(z.x, z.x, yy);
     const double d2 = fmin(z2, fma(xs, xs, yy));
-    return (dz2 <= MLM_NEWTON_TOL2 * d2) || (dz2 >= prev4 && dz2 <= 1e-14 * z2);
+    // 1e-28 z2: a step of ~50 ulp of |z| is the end of the road whatever d is (a root that sits 5e-8
+    // from the secondary when the source is almost behind it)
+    return (dz2 <= fmax(MLM_NEWTON_TOL2 * d2, 1e-28 * z2)) || (dz2 >= prev4 && dz2 <= 1e-14 * z2);
 }
 
 // p, p' at x for the full quintic
@@ -352,7 +354,7 @@ MLM_HD int solve_roots(const cd c[6], double s, cd z[5], unsigned& flags) {
             cd zk = z[k];
             double prev = 1e300;
 #pragma unroll 1
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < 8; ++j) {
                 cd p, dp;
                 horner2(c, zk, p, dp);
                 MLM_COUNT(newton_evals);
@@ -362,7 +364,7 @@ MLM_HD int solve_roots(const cd c[6], double s, cd z[5], unsigned& flags) {
                 zk = zk - dz;
                 if (newton_stop(dz2, prev, zk, s)) break;
                 prev = 0.25 * dz2;
-                if (j == 3) flags |= MLM_FLAG_NOCONV;
+                if (j == 7) flags |= MLM_FLAG_NOCONV;
             }
             z[k] = zk;
         }

@@ -460,3 +460,89 @@ def test_full_size_properties(mb):
     assert ((top["flags"] & 3) == 0).all()
     f5 = float((top["nimg"] == 5).mean())
     assert 0.05 < f5 < 0.6
+
+
+# ---- BASELINE.json configurations at FULL size -----------------------------------------------------
+def _sample_map_vs_oracle(mb, m, s, q, rho, G, x0, y0, dx, dy, nx, ny, nsample, seed):
+    from oracle import cassan_oracle as oracle
+    rng = np.random.default_rng(seed)
+    idx = rng.integers(0, nx * ny, nsample)
+    r, c = np.divmod(idx, nx)
+    zeta = ((x0 + (c + 0.5) * dx) + (-(s * q / (1. + q)))) + 1j * (y0 + (r + 0.5) * dy)
+    nb, B0, B2, B4, z, keep, minJ, res = oracle.batch_a4(s, q, rho, G, zeta, return_extra=True)
+    ref_A = np.stack([B0, B2, B4], 1)
+    mask = parity.mask_from_reference(ref_A, res, minJ)
+    got_A = np.stack([m["A0"].ravel()[idx], m["A2"].ravel()[idx], m["A4"].ravel()[idx]], 1)
+    par = [(s, q, rho, G)] * nsample
+    return parity.compare(m["nimg"].ravel()[idx], got_A, nb, ref_A, mask, truth_fn=truth_fn_factory(par, zeta))
+
+
+@pytest.mark.parametrize("name,s,q,cx,half,n", [("C4", 1.0, 0.5, -0.08, 0.80, 8192), ("C3", 0.8, 0.1, 0.11, 0.75, 4096)])
+def test_full_size_maps_sampled_against_oracle(mb, name, s, q, cx, half, n):
+    """The whole 8192^2 / 4096^2 map of BASELINE.json through the public host API; 40 000 random pixels
+    of it against the oracle (same parity rules), plus whole-map invariants."""
+    rho, G = 1e-3, 0.5
+    x0, y0, dx, dy = cx - half, -half, 2 * half / n, 2 * half / n
+    m = mb.magnification_map(s, q, rho, G, x0, y0, dx, dy, n, n)
+    rep = _sample_map_vs_oracle(mb, m, s, q, rho, G, x0, y0, dx, dy, n, n, 40000, 2024)
+    print(name, "full-size sampled parity:", rep)
+    assert rep["masked_frac"] < 0.01
+    assert set(np.unique(m["nimg"])) <= {3, 5}
+    assert ((m["flags"] & 3) == 0).all()                    # no iteration cap hit anywhere on the map
+    assert m["A0"].min() >= 1.0 and np.isfinite(m["A4"]).all()
+    assert (m["flags"] != 0).mean() < 0.01
+
+
+def test_full_size_C2_lightcurve(mb):
+    """1e6 epochs (BASELINE configs[1]): tracked light-curve kernel vs cold-solved points on every epoch,
+    and 30 000 of them against the oracle."""
+    from oracle import cassan_oracle as oracle
+    s, q, rho, G = 1.0, 1e-3, 1e-3, 0.5
+    T = 1000000
+    dtau = 4.0 / T
+    zeta = mb.lightcurve_coordinates(s, q, 0.01, 0.35, -2.0, dtau, T)
+    p = mb.magnification_points(s, q, rho, G, zeta)
+    mm = mb.magnification_models([s], [q], [rho], [G], [0.01], [0.35], -2.0, dtau, T)
+    assert np.array_equal(mm["nimg"][0], p["nimg"])
+    ok = (mm["flags"][0] == 0) & (p["flags"] == 0)
+    assert ok.mean() > 0.99
+    for k in ("A0", "A2", "A4"):
+        assert np.abs(mm[k][0] / p[k] - 1)[ok].max() < 1e-9, k
+    assert ((mm["flags"] & 3) == 0).all() and ((p["flags"] & 3) == 0).all()
+    idx = np.sort(np.random.default_rng(5).integers(0, T, 30000))
+    nb, B0, B2, B4, z, keep, minJ, res = oracle.batch_a4(s, q, rho, G, zeta[idx], return_extra=True)
+    ref_A = np.stack([B0, B2, B4], 1)
+    got_A = np.stack([mm["A0"][0][idx], mm["A2"][0][idx], mm["A4"][0][idx]], 1)
+    rep = parity.compare(mm["nimg"][0][idx], got_A, nb, ref_A, parity.mask_from_reference(ref_A, res, minJ),
+                         truth_fn=truth_fn_factory([(s, q, rho, G)] * len(idx), zeta[idx]))
+    print("C2 full-size parity:", rep)
+
+
+def test_full_size_C5_model_grid(mb):
+    """1e4 models x 2000 epochs (BASELINE configs[4]): whole-grid invariants, 40 models against the cold
+    point solver and 6 models against the oracle."""
+    from oracle import cassan_oracle as oracle
+    rng = np.random.default_rng(20240517)
+    M, T = 10000, 2000
+    s = np.exp(rng.uniform(np.log(0.5), np.log(2.), M))
+    q = np.exp(rng.uniform(np.log(1e-4), np.log(1.), M))
+    rho = np.exp(rng.uniform(np.log(1e-4), np.log(1e-2), M))
+    G = np.full(M, 0.5)
+    u0, al = rng.uniform(-.5, .5, M), rng.uniform(0, 2 * np.pi, M)
+    r = mb.magnification_models(s, q, rho, G, u0, al, -2.0, 4.0 / T, T)
+    assert set(np.unique(r["nimg"])) <= {3, 5}
+    assert ((r["flags"] & 3) == 0).all()
+    assert r["A0"].min() >= 1.0 and np.isfinite(r["A4"]).all()
+    pick = rng.choice(M, 40, replace=False)
+    for j, m in enumerate(pick):
+        zeta = mb.lightcurve_coordinates(s[m], q[m], u0[m], al[m], -2.0, 4.0 / T, T)
+        p = mb.magnification_points(s[m], q[m], rho[m], G[m], zeta)
+        assert np.array_equal(p["nimg"], r["nimg"][m]), m
+        ok = (p["flags"] == 0) & (r["flags"][m] == 0)
+        assert np.abs(r["A4"][m] / p["A4"] - 1)[ok].max() < 1e-9, m
+        if j < 6:
+            nb, B0, B2, B4, z, keep, minJ, res = oracle.batch_a4(s[m], q[m], rho[m], G[m], zeta, return_extra=True)
+            ref_A = np.stack([B0, B2, B4], 1)
+            got_A = np.stack([r["A0"][m], r["A2"][m], r["A4"][m]], 1)
+            parity.compare(r["nimg"][m], got_A, nb, ref_A, parity.mask_from_reference(ref_A, res, minJ),
+                           truth_fn=truth_fn_factory([(s[m], q[m], rho[m], G[m])] * T, zeta), max_adjudicate=600)
