@@ -1,9 +1,11 @@
 """Dev script: host-emulated kernel logic vs golden fixtures (reference) and truth."""
+import os as _os
+_ROOT = _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))
 import ctypes, sys, os
 import numpy as np
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, _ROOT)
 from oracle import cassan_oracle as o
-lib = ctypes.CDLL('/root/repo/tests/host_emu/libmlm_emu.so')
+lib = ctypes.CDLL(_ROOT + '/tests/host_emu/libmlm_emu.so')
 dp = ctypes.POINTER(ctypes.c_double); up = ctypes.POINTER(ctypes.c_ubyte)
 def P(a): return a.ctypes.data_as(dp)
 def U(a): return a.ctypes.data_as(up)
@@ -28,7 +30,7 @@ if __name__=="__main__":
         out=np.zeros((200,3))
         lib.emu_image_terms(P(W.view(np.float64)),ctypes.c_long(200),ctypes.c_int(lit),P(out))
         print('literal' if lit else 'wirtinger', np.abs(out[:,0]/mu0-1).max(), np.abs(out[:,1]/mu2-1).max(), np.abs(out[:,2]/mu4-1).max())
-    g=np.load('/root/repo/tests/golden/golden_points.npz')
+    g=np.load(_ROOT + '/tests/golden/golden_points.npz')
     tags=g['tags']; par=g['params']; zeta=g['zeta']
     res=np.zeros((len(tags),3)); ni=np.zeros(len(tags),int); fl=np.zeros(len(tags),int)
     # group by params

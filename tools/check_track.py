@@ -1,9 +1,11 @@
 """Dev script: warm-started column strips (host emulation of k_map's control flow) vs cold solves."""
+import os as _os
+_ROOT = _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))
 import ctypes, sys
 import numpy as np
-sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tools')
+sys.path.insert(0,_ROOT); sys.path.insert(0,_ROOT + '/tools')
 import check_emu as ce
-libs = ctypes.CDLL('/root/repo/tests/host_emu/libmlm_emu_stats.so')
+libs = ctypes.CDLL(_ROOT + '/tests/host_emu/libmlm_emu_stats.so')
 dp=ctypes.POINTER(ctypes.c_double); up=ctypes.POINTER(ctypes.c_ubyte)
 def strip(s,q,rho,G,zeta,L):
     zeta=np.ascontiguousarray(zeta,dtype=np.complex128); n=zeta.size

@@ -1,8 +1,10 @@
 """Prototype: closed-form Laplacian / bi-Laplacian of the image magnification (operator form) vs the
 oracle's literal (xi, eta) recursion.  D = d_z + w d_zbar, Dbar = wbar d_z + d_zbar, d_zeta = mu D."""
+import os as _os
+_ROOT = _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))
 import sys
 import numpy as np
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, _ROOT)
 from oracle import cassan_oracle as o
 
 

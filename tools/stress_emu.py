@@ -1,10 +1,12 @@
 """Dev script: large random comparison of the host-emulated kernel logic vs batch oracle."""
+import os as _os
+_ROOT = _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))
 import ctypes, sys, time
 import numpy as np
-sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tools')
+sys.path.insert(0,_ROOT); sys.path.insert(0,_ROOT + '/tools')
 from oracle import cassan_oracle as o
 import check_emu as ce
-libs = ctypes.CDLL('/root/repo/tests/host_emu/libmlm_emu_stats.so')
+libs = ctypes.CDLL(_ROOT + '/tests/host_emu/libmlm_emu_stats.so')
 def run(name,s,q,rho,G,zeta):
     ce.lib = libs
     st=np.zeros(2,np.int64); libs.emu_stats(st.ctypes.data_as(ctypes.POINTER(ctypes.c_long)),1)

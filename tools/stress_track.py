@@ -1,8 +1,10 @@
 """Dev script: warm-started segments (host emulation of k_models / k_map control flow) vs cold solves on
 random C5-like models (log-uniform s, q, rho) -- image counts must match, values agree to 1e-9."""
+import os as _os
+_ROOT = _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))
 import sys
 import numpy as np
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tools')
+sys.path.insert(0, _ROOT); sys.path.insert(0, _ROOT + '/tools')
 import check_track as ct, check_emu as ce
 from microlensing_b200.batched import lightcurve_coordinates
 ce.lib = ct.libs
