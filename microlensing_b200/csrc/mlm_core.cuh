@@ -433,7 +433,10 @@ MLM_HD bool track_roots(const cd c[6], double s, cd z[5]) {
 // 1: warm start from sz, 2: warm start from the linear extrapolation 2 sz - szp, which cuts the
 // initial error from O(h) to O(h^2) and the Newton work to ~1 step per root).  Falls back to
 // the cold solve whenever tracking is rejected.  Returns the new hist.
-MLM_HD int advance_roots(const cd c[6], double s, cd* sz, cd* szp, int stride, int hist, unsigned& flags) {
+// `ratio` = (this step of the source) / (previous step) for unevenly spaced sequences (1 on maps
+// and uniform light curves): the extrapolation is z + ratio (z - z_prev).
+MLM_HD int advance_roots(const cd c[6], double s, cd* sz, cd* szp, int stride, int hist, unsigned& flags,
+                         double ratio = 1.0) {
     cd z[5];
     if (hist >= 1) {
 #pragma unroll
@@ -442,7 +445,8 @@ MLM_HD int advance_roots(const cd c[6], double s, cd* sz, cd* szp, int stride, i
             cd pred = zc;
             if (hist >= 2) {
                 const cd zo = szp[k * stride];
-                pred = mk(fma(2.0, zc.x, -zo.x), fma(2.0, zc.y, -zo.y));
+                if (ratio == 1.0) pred = mk(fma(2.0, zc.x, -zo.x), fma(2.0, zc.y, -zo.y));
+                else pred = mk(fma(ratio, zc.x - zo.x, zc.x), fma(ratio, zc.y - zo.y, zc.y));
             }
             szp[k * stride] = zc;
             z[k] = pred;

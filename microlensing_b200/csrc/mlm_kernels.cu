@@ -43,26 +43,48 @@ __device__ __forceinline__ void store_result(const PointResult& r, int64_t i, do
     if (flags) flags[i] = (uint8_t)r.flags;
 }
 
-// K1a: arbitrary list of positions, one lens.
+// K1a: list of positions, one lens.  A thread owns `seg` CONSECUTIVE list entries: when the list is a
+// coherent sequence (a light curve along any trajectory, a scan line) it walks along it with
+// warm-started root tracking, the extrapolation scaled by the ratio of successive source steps;
+// entries that are far from their predecessor (> 0.1 Einstein radii), or whose tracking is
+// rejected, are solved cold, so an unordered list costs what it did before.  seg is a function of n
+// only; the 16-byte loads of a warp are seg entries apart (sector-granular, the path is compute-bound).
 template <int ORDER>
-__global__ void __launch_bounds__(MLM_BLOCK)
+__global__ void __launch_bounds__(MLM_BLOCK, 4)
 k_points(const __grid_constant__ LensTable T, const SourceFactors sf, const double2* __restrict__ zeta, int64_t n,
-         double* __restrict__ A0, double* __restrict__ A2, double* __restrict__ A4, uint8_t* __restrict__ nimg,
-         uint8_t* __restrict__ flags) {
-    const int64_t i = (int64_t)blockIdx.x * MLM_BLOCK + threadIdx.x;
-    if (i >= n) return;
-    const double2 zz = __ldg(zeta + i);               // one 16-byte load per thread, coalesced
-    __shared__ cd s_roots[5][MLM_BLOCK];
+         int seg, double* __restrict__ A0, double* __restrict__ A2, double* __restrict__ A4,
+         uint8_t* __restrict__ nimg, uint8_t* __restrict__ flags) {
+    __shared__ cd s_roots[2][5][MLM_BLOCK];
     __shared__ cd s_rcp[10][MLM_BLOCK];
-    cd* const sz = &s_roots[0][threadIdx.x];
-    const cd zt = mk(zz.x, zz.y);
-    cd c[6];
-    PointResult r;
-    r.flags = 0;
-    lens_polynomial(T, zt, c);
-    advance_roots(c, T.s, sz, sz, MLM_BLOCK, 0, r.flags);  // hist = 0: cold solve
-    accumulate_images<ORDER>(T, sf, zt, sz, MLM_BLOCK, &s_rcp[0][threadIdx.x], MLM_BLOCK, r);
-    store_result(r, i, A0, A2, A4, nimg, flags);
+    cd* const sz = &s_roots[0][0][threadIdx.x];
+    cd* const szp = &s_roots[1][0][threadIdx.x];
+    const int64_t i0 = ((int64_t)blockIdx.x * MLM_BLOCK + threadIdx.x) * seg;
+    if (i0 >= n) return;
+    const int64_t i1 = (i0 + seg < n) ? i0 + seg : n;
+    int hist = 0;
+    cd zprev = mk(0.0, 0.0), dprev = mk(0.0, 0.0);
+    for (int64_t i = i0; i < i1; ++i) {
+        const double2 zz = __ldg(zeta + i);
+        const cd zt = mk(zz.x, zz.y);
+        const cd d = zt - zprev;
+        const double d2 = norm2(d);
+        double ratio = 1.0;
+        if (hist >= 1 && !(d2 <= 1e-2)) hist = 0;                 // jump (or NaN): start afresh
+        if (hist >= 2) {
+            // projection of this step on the previous one; a sensible extrapolation only for 0 < ratio < 4
+            ratio = re_mulc(d, dprev) * rcp(norm2(dprev));
+            if (!(ratio > 0.0 && ratio < 4.0)) hist = 1;
+        }
+        cd c[6];
+        PointResult r;
+        r.flags = 0;
+        lens_polynomial(T, zt, c);
+        hist = advance_roots(c, T.s, sz, szp, MLM_BLOCK, hist, r.flags, ratio);
+        accumulate_images<ORDER>(T, sf, zt, sz, MLM_BLOCK, &s_rcp[0][threadIdx.x], MLM_BLOCK, r);
+        store_result(r, i, A0, A2, A4, nimg, flags);
+        zprev = zt;
+        dprev = d;
+    }
 }
 
 // K1b: magnification map, zeta generated in-kernel (no input traffic).
@@ -387,6 +409,7 @@ struct mlm_context {
     std::string err;
     int sm_count = 148;
     int map_strip = 64;                                // rows per warm-start strip of k_map (MLM_MAP_STRIP)
+    int points_segment = 0;                            // consecutive list entries per thread of k_points (0: from n; MLM_POINTS_SEGMENT)
     int models_segment = 0;                            // epochs per warm-start segment of k_models (0: from T; MLM_SEGMENT)
 };
 
@@ -474,6 +497,10 @@ int mlm_create(int device, mlm_context** out) {
     if (const char* e2 = getenv("MLM_MAP_STRIP")) {
         const int v = atoi(e2);
         if (v >= 1 && v <= 4096) ctx->map_strip = v;
+    }
+    if (const char* e4 = getenv("MLM_POINTS_SEGMENT")) {
+        const int v = atoi(e4);
+        if (v >= 1 && v <= 65536) ctx->points_segment = v;
     }
     if (const char* e3 = getenv("MLM_SEGMENT")) {
         const int v = atoi(e3);
@@ -592,12 +619,16 @@ int mlm_points(mlm_context* ctx, double s, double q, double rho, double Gamma, c
     LensTable T;
     make_table(s, q, &T);
     const SourceFactors sf = source_factors(rho, Gamma);
-    const unsigned blocks = (unsigned)((n + MLM_BLOCK - 1) / MLM_BLOCK);
+    // consecutive entries per thread: enough threads to fill the GPU (148 SMs x 16 warps) first
+    int seg = ctx->points_segment > 0 ? ctx->points_segment : (int)(n / (148 * 16 * 32));
+    if (ctx->points_segment <= 0) seg = seg < 1 ? 1 : (seg > 32 ? 32 : seg);
+    const int64_t nthreads = (n + seg - 1) / seg;
+    const unsigned blocks = (unsigned)((nthreads + MLM_BLOCK - 1) / MLM_BLOCK);
     cudaStream_t st = pick(ctx, stream);
     if (order == 4)
-        k_points<4><<<blocks, MLM_BLOCK, 0, st>>>(T, sf, (const double2*)zeta, n, A0, A2, A4, nimg, flags);
+        k_points<4><<<blocks, MLM_BLOCK, 0, st>>>(T, sf, (const double2*)zeta, n, seg, A0, A2, A4, nimg, flags);
     else
-        k_points<2><<<blocks, MLM_BLOCK, 0, st>>>(T, sf, (const double2*)zeta, n, A0, A2, A4, nimg, flags);
+        k_points<2><<<blocks, MLM_BLOCK, 0, st>>>(T, sf, (const double2*)zeta, n, seg, A0, A2, A4, nimg, flags);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -846,8 +877,9 @@ int mlm_points_host(mlm_context* ctx, double s, double q, double rho, double Gam
     if (rc) return rc;
     // chunks alternate between the two streams: H2D(k+1) and D2H(k-1) overlap kernel(k)
     int k = 0;
-    for (int64_t off = 0; off < n; off += MLM_CHUNK_POINTS, ++k) {
-        const int64_t cnt = (n - off < MLM_CHUNK_POINTS) ? (n - off) : MLM_CHUNK_POINTS;
+    const int64_t chunk = (n / 8 > MLM_CHUNK_POINTS) ? (n + 7) / 8 : MLM_CHUNK_POINTS;   // at most ~8 chunks
+    for (int64_t off = 0; off < n; off += chunk, ++k) {
+        const int64_t cnt = (n - off < chunk) ? (n - off) : chunk;
         cudaStream_t st = ctx->stream[k & 1];
         CK(cudaMemcpyAsync(sc.zeta + 2 * off, zeta + 2 * off, cnt * 16, cudaMemcpyHostToDevice, st));
         rc = mlm_points(ctx, s, q, rho, Gamma, sc.zeta + 2 * off, cnt, order, A0 ? sc.A0 + off : nullptr,

@@ -183,6 +183,36 @@ def test_lightcurve_C2_vs_oracle(mb):
     assert (mm["flags"] & 3).sum() == 0
 
 
+@pytest.mark.parametrize("s,q", [(0.8, 0.1), (1.0, 1e-3)])
+def test_points_on_an_uneven_curved_trajectory(mb, s, q):
+    """magnification_points walks consecutive list entries with warm-started tracking (extrapolation
+    scaled by the ratio of successive source steps): unevenly sampled, curved trajectory with gaps and a
+    shuffled copy of the same positions (no coherence at all) against the oracle."""
+    from oracle import cassan_oracle as oracle
+    rho, G = 1e-3, 0.5
+    rng = np.random.default_rng(3)
+    n = 30000
+    tau = np.cumsum(rng.exponential(1.0, n))
+    tau = -1.5 + 3.0 * tau / tau[-1]                                   # uneven epochs
+    tau[n // 3:] += 0.2                                                # a gap (jump > 0.1 -> cold restart)
+    zeta_cm = (tau + 1j * (0.02 + 0.05 * tau ** 2)) * np.exp(0.3j)      # curved
+    zeta = zeta_cm - s * q / (1 + q)
+    nb, B0, B2, B4, z, keep, minJ, res = oracle.batch_a4(s, q, rho, G, zeta, return_extra=True)
+    ref_A = np.stack([B0, B2, B4], 1)
+    mask = parity.mask_from_reference(ref_A, res, minJ)
+    par = [(s, q, rho, G)] * n
+    r = mb.magnification_points(s, q, rho, G, zeta)
+    rep = parity.compare(r["nimg"], np.stack([r["A0"], r["A2"], r["A4"]], 1), nb, ref_A, mask,
+                         truth_fn=truth_fn_factory(par, zeta))
+    print("uneven trajectory parity:", rep)
+    assert (r["flags"] & 3).sum() == 0
+    perm = rng.permutation(n)
+    rs = mb.magnification_points(s, q, rho, G, zeta[perm])
+    assert np.array_equal(rs["nimg"], r["nimg"][perm])
+    ok = (rs["flags"] == 0) & (r["flags"][perm] == 0)
+    assert np.abs(rs["A4"] / r["A4"][perm] - 1)[ok].max() < 1e-9
+
+
 def test_models_C5_sample_vs_oracle(mb):
     from oracle import cassan_oracle as oracle
     rng = np.random.default_rng(20240517)
