@@ -585,11 +585,19 @@ MLM_HD void accumulate_images(const LensTable& T, const SourceFactors sf, cd zet
         if (f2 < 1e-2) cand |= 1u << k;               // NaN residual -> rejected, like NumPy
     }
     // Pass 2, rolled over the candidates (5 x ~350 instructions would overflow the instruction
-    // cache); roots and reciprocals are read back from memory, so no register array is indexed
+    // cache).  Each lane walks ITS OWN candidate list (lowest set bit of `cand` first), so a warp runs
+    // max-over-lanes(#candidates) iterations even when the physical images sit at different root
+    // indices in different lanes (lanes of a light-curve kernel are far-apart epochs).  Roots and
+    // reciprocals are read back from memory with a per-lane index: no register array is indexed
     // dynamically and they occupy no registers meanwhile.
 #pragma unroll 1
-    for (int k = 0; k < 5; ++k) {
-        if (!((cand >> k) & 1u)) continue;
+    while (cand) {
+#if defined(__CUDA_ARCH__)
+        const int k = __ffs((int)cand) - 1;
+#else
+        const int k = __builtin_ctz(cand);
+#endif
+        cand &= cand - 1u;
         cd zk = z[k * zstride];
         cd zs = mk(zk.x + T.s, zk.y);
         cd r1 = scratch[(2 * k) * sstride], r2 = scratch[(2 * k + 1) * sstride];
