@@ -20,7 +20,8 @@ from __future__ import annotations
 
 from dataclasses import dataclass
 
-__all__ = ["shard_range", "ShardPlan", "plan_map", "full_map_layout", "auto_strip", "BYTES_PER_POSITION", "KEYS", "ShardedMap"]
+__all__ = ["shard_range", "ShardPlan", "plan_map", "full_map_layout", "auto_strip", "BYTES_PER_POSITION", "KEYS", "ShardedMap",
+           "ShardedModels"]
 
 BYTES_PER_POSITION = 26           # 3 x float64 + 2 x uint8
 KEYS = (("A0", 8), ("A2", 8), ("A4", 8), ("nimg", 1), ("flags", 1))     # output arrays and their item sizes
@@ -316,3 +317,115 @@ class _null:
 
     def __exit__(self, *a):
         return False
+
+
+class ShardedModels:
+    """Model grid (M models x T epochs of a straight trajectory) sharded by contiguous model ranges over
+    the ranks (BASELINE.json configs[4]), results on rank 0.
+
+    fit=None : the M x T magnifications (26 B per epoch, or the `outputs` subset) are written by every
+               rank's kernel straight into rank 0's buffer (same fused peer-store gather as ShardedMap).
+    fit=(flux, sigma): the light-curve fit is fused into the kernel (mlm_models_chi2); only 8 doubles per
+               model travel.
+    A model's light curve does not depend on which rank computes it (the segment length of the kernel
+    is a function of T only), so the result is bit-identical to the single-GPU one.
+    """
+
+    STAT_KEYS = ("chi2", "Fs", "Fb", "SA", "SAA", "SAF", "n5", "nflag")
+
+    def __init__(self, params, tau0: float, dtau: float, T: int, rank: int = 0, world: int = 1, device=None,
+                 group=None, outputs=None, fit=None):
+        import numpy as np
+        import torch
+        import torch.distributed as dist
+        from . import _capi
+        self.torch = torch
+        self.rank, self.world, self.group = rank, world, group
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.tau0, self.dtau, self.T = float(tau0), float(dtau), int(T)
+        arrs = [np.ascontiguousarray(np.asarray(a, dtype=np.float64)).ravel() for a in params]   # s,q,rho,Gamma,u0,alpha
+        if len(arrs) != 6 or any(a.size != arrs[0].size for a in arrs):
+            raise ValueError("params = (s, q, rho, Gamma, u0, alpha), arrays of equal length M")
+        self.M = arrs[0].size
+        self.lo, self.hi = shard_range(self.M, rank, world)
+        self.par = [torch.from_numpy(a[self.lo:self.hi].copy()).to(self.device) for a in arrs]
+        self.outputs = tuple(k for k, _ in KEYS) if outputs is None else tuple(outputs)
+        self.fit = None
+        ctx = _capi.context(self.device.index)
+        if fit is not None:
+            flux = np.ascontiguousarray(fit[0], dtype=np.float64).ravel()
+            sigma = np.ascontiguousarray(np.broadcast_to(np.asarray(fit[1], dtype=np.float64), flux.shape))
+            if flux.size != self.T:
+                raise ValueError("fit = (flux, sigma) with T entries")
+            self.fit = (torch.from_numpy(flux).to(self.device), torch.from_numpy(1.0 / sigma ** 2).to(self.device))
+            layout, nbytes = {"stats": 0}, self.M * 8 * 8
+        else:
+            layout, nbytes = full_map_layout(self.T, self.M)              # (M, T) arrays, row = model
+        nbytes = max(nbytes, 256)
+        # rank 0 owns the result buffer; the others map it (CUDA IPC) and address their model rows in it
+        box = [None]
+        if rank == 0:
+            base = ctx.device_alloc(nbytes)
+            if world > 1:
+                box[0] = ctx.ipc_export(base)
+        if world > 1:
+            dist.broadcast_object_list(box, src=0, group=group)
+            if rank != 0:
+                base = ctx.ipc_open(box[0])
+        self._buf = (ctx, base, rank == 0)
+        self.layout, self.nbytes = layout, nbytes
+        self.full = None
+        if rank == 0:
+            raw = torch.as_tensor(_DevMem(base, nbytes), device=self.device)
+            if self.fit is not None:
+                self.full = {"stats": raw[: self.M * 64].view(torch.float64).view(self.M, 8)}
+            else:
+                n = self.M * self.T
+                self.full = {key: raw[layout[key]: layout[key] + n * item].view(torch.float64 if item == 8 else torch.uint8)
+                             .view(self.M, self.T) for key, item in KEYS}
+        self._fence = torch.zeros(1, dtype=torch.float32, device=self.device) if world > 1 else None
+
+    def compute(self, order=4):
+        """Enqueue this rank's models on the current stream (results land in rank 0's buffer)."""
+        import torch.distributed as dist
+        from .batched import models_device, models_chi2_device
+        ctx, base, _ = self._buf
+        st = self.torch.cuda.current_stream(self.device).cuda_stream
+        m = self.hi - self.lo
+        if m:
+            if self.fit is not None:
+                models_chi2_device(*self.par, m, self.tau0, self.dtau, self.T, self.fit[0], self.fit[1],
+                                   base + self.lo * 64, order=order, stream=st, device=self.device.index)
+            else:
+                ptr = {key: (base + self.layout[key] + self.lo * self.T * item if key in self.outputs else None)
+                       for key, item in KEYS}
+                models_device(*self.par, m, self.tau0, self.dtau, self.T, ptr["A0"], ptr["A2"], ptr["A4"], ptr["nimg"],
+                              ptr["flags"], order=order, stream=st, device=self.device.index)
+        if self.world > 1:
+            dist.all_reduce(self._fence, group=self.group)          # stream-ordered completion fence
+
+    def result_host(self):
+        """Rank 0: numpy arrays ((M, T) magnifications or the per-model fit statistics); None elsewhere."""
+        if self.rank != 0:
+            return None
+        self.torch.cuda.synchronize(self.device)
+        if self.fit is not None:
+            st = self.full["stats"].cpu().numpy()
+            return {k: st[:, i].copy() for i, k in enumerate(self.STAT_KEYS)}
+        return {k: v.cpu().numpy() for k, v in self.full.items() if k in self.outputs}
+
+    def close(self):
+        """Collective: every rank unmaps before rank 0 frees."""
+        if self._buf is None:
+            return
+        import torch.distributed as dist
+        ctx, base, owner = self._buf
+        self._buf = None
+        self.full = None
+        self.torch.cuda.synchronize(self.device)
+        if not owner:
+            ctx.ipc_close(base)
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        if owner:
+            ctx.device_free(base)

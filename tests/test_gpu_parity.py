@@ -466,6 +466,76 @@ def test_two_gpu_sharded_map_equals_single_gpu(mb, tmp_path, gather, layout):
     assert np.abs(got["A4"] / default["A4"] - 1)[ok].max() < 1e-9
 
 
+def _two_gpu_models_worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    os.environ["MLM_DEVICE"] = str(rank)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    try:
+        from microlensing_b200.sharding import ShardedModels
+        par, T, flux, sigma = _model_grid_case()
+        sm = ShardedModels(par, -2.0, 4.0 / T, T, rank, world)
+        sm.compute()
+        res = sm.result_host()
+        sf = ShardedModels(par, -2.0, 4.0 / T, T, rank, world, fit=(flux, sigma))
+        sf.compute()
+        fit = sf.result_host()
+        if rank == 0:
+            np.savez(os.path.join(out_dir, "models.npz"), **res, **{"fit_" + k: v for k, v in fit.items()})
+        dist.barrier()
+        sm.close()
+        sf.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def _model_grid_case():
+    rng = np.random.default_rng(77)
+    M, T = 37, 500
+    s = np.exp(rng.uniform(np.log(0.5), np.log(2.), M))
+    q = np.exp(rng.uniform(np.log(1e-4), np.log(1.), M))
+    rho = np.exp(rng.uniform(np.log(1e-4), np.log(1e-2), M))
+    par = (s, q, rho, np.full(M, 0.5), rng.uniform(-.5, .5, M), rng.uniform(0, 2 * np.pi, M))
+    flux = 1.0 + rng.random(T)
+    return par, T, flux, np.full(T, 0.05)
+
+
+def test_sharded_models_single_and_two_gpu(mb, tmp_path):
+    """Model-sharded grid (BASELINE configs[4]): ShardedModels on 1 rank, and on 2 ranks when 2 GPUs are
+    visible, equals the plain host API bit for bit (magnifications and fused fit statistics)."""
+    import torch
+    from microlensing_b200.sharding import ShardedModels
+    par, T, flux, sigma = _model_grid_case()
+    one = mb.magnification_models(*par, -2.0, 4.0 / T, T)
+    fit1 = mb.models_chi2(*par, -2.0, 4.0 / T, flux, sigma)
+    sm = ShardedModels(par, -2.0, 4.0 / T, T)
+    sm.compute()
+    res = sm.result_host()
+    sf = ShardedModels(par, -2.0, 4.0 / T, T, fit=(flux, sigma))
+    sf.compute()
+    fit = sf.result_host()
+    sm.close(); sf.close()
+    for k in ("A0", "A2", "A4", "nimg", "flags"):
+        assert np.array_equal(res[k], one[k]), k
+    for k in ShardedModels.STAT_KEYS:
+        assert np.array_equal(fit[k], fit1[k]), k
+    if torch.cuda.device_count() < 2:
+        return
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    mp.spawn(_two_gpu_models_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    got = np.load(tmp_path / "models.npz")
+    for k in ("A0", "A2", "A4", "nimg", "flags"):
+        assert np.array_equal(got[k], one[k]), k
+    for k in ShardedModels.STAT_KEYS:
+        assert np.array_equal(got["fit_" + k], fit1[k]), k
+
+
 def test_full_size_properties(mb):
     """BASELINE sizes through size-independent properties: the lens is symmetric about the real
     axis, so a map whose window is symmetric in y equals its own vertical mirror; image counts are
