@@ -237,6 +237,8 @@ def bench_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; microlensing_b200 has no CPU fallback")
     cfg = CONFIGS[args.config]
+    if cfg["kind"] == "models":
+        return bench_models(args)
     if args.nx:
         cfg = dict(cfg, nx=args.nx, ny=args.nx)
     base = None
@@ -543,6 +545,104 @@ def other_configs(mb, dev, reps=3):
                                                       "h2d_bytes": int(8 * (6 * M + 2 * T)), "d2h_bytes": int(64 * M),
                                                       "best_model": int(np.argmin(r["chi2"]))}
     return out
+
+
+def bench_models(args):
+    """--config C5: the 1e4 x 2000 model grid, models sharded over the ranks, results gathered to rank 0
+    by peer stores (magnifications) or as fused fit statistics.  A parity-test configuration of
+    BASELINE.json, timed for information (the headline is the C4 map)."""
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    os.environ["MLM_DEVICE"] = str(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    import microlensing_b200 as mb
+    from microlensing_b200 import _capi
+    from microlensing_b200.sharding import ShardedModels, shard_range
+    c = CONFIGS["C5"]
+    rng = np.random.default_rng(c["seed"])
+    M, T = c["M"], c["T"]
+    par = (np.exp(rng.uniform(np.log(0.5), np.log(2.), M)), np.exp(rng.uniform(np.log(1e-4), np.log(1.), M)),
+           np.exp(rng.uniform(np.log(1e-4), np.log(1e-2), M)), np.full(M, 0.5), rng.uniform(-.5, .5, M),
+           rng.uniform(0, 2 * np.pi, M))
+    dev = torch.device("cuda", local)
+    ctx = _capi.context(local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(obj):
+        for _ in range(args.warmup):
+            obj.compute()
+        barrier()
+        l0 = ctx.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            obj.compute()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), ctx.launch_count() - l0
+
+    sm = ShardedModels(par, -2.0, 4.0 / T, T, rank, world, device=dev)
+    ms, launches = timed(sm)
+    flux = None
+    if rank == 0:
+        flux = 2.0 * sm.full["A4"][0].cpu().numpy() + 0.5
+    box = [flux]
+    if world > 1:
+        dist.broadcast_object_list(box, src=0)
+    flux = box[0]
+    sm.close()
+    sf = ShardedModels(par, -2.0, 4.0 / T, T, rank, world, device=dev, fit=(flux, np.full(T, 0.01)))
+    ms_fit, _ = timed(sf)
+    best = int(np.argmin(sf.result_host()["chi2"])) if rank == 0 else None
+    sf.close()
+    # end to end through the host API on this rank's models (26 B per epoch back over PCIe)
+    lo, hi = shard_range(M, rank, world)
+    sl = [a[lo:hi] for a in par]
+    out = mb.alloc_outputs((hi - lo, T), device=local, pinned=True)
+    mb.magnification_models(*sl, -2.0, 4.0 / T, T, out=out, device=local)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        mb.magnification_models(*sl, -2.0, 4.0 / T, T, out=out, device=local)
+    te = torch.tensor([(time.perf_counter() - t0) / 3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        n = M * T
+        print(json.dumps({
+            "metric": "A4 magnifications/sec (FP64, model grid 1e4 x 2000)", "value": n / (ms * 1e-3), "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"C5: batched fit grid {M} models x {T} epochs, rng seed {c['seed']}, log-uniform "
+                                   "s in [0.5,2], q in [1e-4,1], rho in [1e-4,1e-2], Gamma 0.5; models sharded "
+                                   f"contiguously over {world} rank(s), results stored into rank 0 by the kernels",
+                       "positions": n, "order": 4},
+            "fused_fit": {"value": n / (ms_fit * 1e-3), "ms_per_step": ms_fit, "bytes_to_rank0_per_model": 64,
+                          "best_model": best},
+            "e2e": {"value": n / float(te[0]), "unit": UNIT, "h2d_bytes_per_step": int(48 * M),
+                    "d2h_bytes_per_step": int(26 * n), "ms_per_step": float(te[0]) * 1e3,
+                    "api": "microlensing_b200.magnification_models"},
+            "gpu_launches": int(launches)}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
 
 
 def _executed_profile():

@@ -157,10 +157,11 @@ k_models(const double* __restrict__ s, const double* __restrict__ q, const doubl
     __shared__ LensTable T;
     __shared__ SourceFactors sf;
     __shared__ double rot[3];                          // cos(alpha), sin(alpha), shift
-    __shared__ cd s_roots[2][5][MLM_MODELS_BLOCK];
+    __shared__ cd s_roots[3][5][MLM_MODELS_BLOCK];
     __shared__ cd s_rcp[10][MLM_MODELS_BLOCK];
     cd* const sz = &s_roots[0][0][threadIdx.x];
     cd* const szp = &s_roots[1][0][threadIdx.x];
+    cd* const szpp = &s_roots[2][0][threadIdx.x];
     const int64_t nseg = (Tn + seg - 1) / seg;
     for (int64_t m = blockIdx.y; m < M; m += gridDim.y) {
         __syncthreads();
@@ -193,7 +194,7 @@ k_models(const double* __restrict__ s, const double* __restrict__ q, const doubl
                 PointResult res;
                 res.flags = 0;
                 lens_polynomial(T, zeta, c);
-                hist = advance_roots(c, T.s, sz, szp, MLM_MODELS_BLOCK, hist, res.flags);
+                hist = advance_roots(c, T.s, sz, szp, MLM_MODELS_BLOCK, hist, res.flags, 1.0, szpp);
                 accumulate_images<ORDER>(T, sf, zeta, sz, MLM_MODELS_BLOCK, &s_rcp[0][threadIdx.x], MLM_MODELS_BLOCK, res);
                 store_result(res, m * Tn + t, A0, A2, A4, nimg, flags);
             }
@@ -216,11 +217,12 @@ k_models_chi2(const double* __restrict__ s, const double* __restrict__ q, const 
     __shared__ LensTable T;
     __shared__ SourceFactors sf;
     __shared__ double rot[3];
-    __shared__ cd s_roots[2][5][MLM_MODELS_BLOCK];
+    __shared__ cd s_roots[3][5][MLM_MODELS_BLOCK];
     __shared__ cd s_rcp[10][MLM_MODELS_BLOCK];
     __shared__ double s_red[8][MLM_MODELS_BLOCK];
     cd* const sz = &s_roots[0][0][threadIdx.x];
     cd* const szp = &s_roots[1][0][threadIdx.x];
+    cd* const szpp = &s_roots[2][0][threadIdx.x];
     const int64_t nseg = (Tn + seg - 1) / seg;
     for (int64_t m = blockIdx.x; m < M; m += gridDim.x) {
         __syncthreads();
@@ -250,7 +252,7 @@ k_models_chi2(const double* __restrict__ s, const double* __restrict__ q, const 
                 PointResult res;
                 res.flags = 0;
                 lens_polynomial(T, zeta, c);
-                hist = advance_roots(c, T.s, sz, szp, MLM_MODELS_BLOCK, hist, res.flags);
+                hist = advance_roots(c, T.s, sz, szp, MLM_MODELS_BLOCK, hist, res.flags, 1.0, szpp);
                 accumulate_images<ORDER>(T, sf, zeta, sz, MLM_MODELS_BLOCK, &s_rcp[0][threadIdx.x], MLM_MODELS_BLOCK, res);
                 const double A = (ORDER >= 4) ? res.A4 : res.A2;
                 const double w = __ldg(weight + t), f = __ldg(flux + t);

@@ -64,13 +64,16 @@ void emu_image_terms(const double* W, long n, int literal, double* mu) {
 }
 
 // column strip of a map with warm-started tracking, same control flow as k_map
+static int g_quadratic = 0;   // 1: three-level history (k_models), 0: two-level (k_map)
+extern "C" void emu_set_quadratic(int on) { g_quadratic = on; }
+
 extern "C" void emu_strip(double s, double q, double rho, double Gamma, const double* zeta, long n, int strip,
                           double* A0, double* A2, double* A4, unsigned char* nimg, unsigned char* flags,
                           long* ncold) {
     LensTable T;
     make_table(s, q, &T);
     SourceFactors sf = source_factors(rho, Gamma);
-    cd z[5], zp[5];
+    cd z[5], zp[5], zpp[5];
     int hist = 0;
     long cold = 0;
     for (long i = 0; i < n; ++i) {
@@ -81,7 +84,7 @@ extern "C" void emu_strip(double s, double q, double rho, double Gamma, const do
         r.flags = 0;
         lens_polynomial(T, zeta_i, c);
         const int before = hist;
-        hist = advance_roots(c, T.s, z, zp, 1, hist, r.flags);
+        hist = advance_roots(c, T.s, z, zp, 1, hist, r.flags, 1.0, g_quadratic ? zpp : nullptr);
         if (before == 0 || hist < 2) ++cold;
         cd scratch[10];
         accumulate_images<4>(T, sf, zeta_i, z, 1, scratch, 1, r);

@@ -151,8 +151,10 @@ def emu(built):
             return r, fl
 
         @staticmethod
-        def strip(s, q, rho, G, zeta, seg):
-            """warm-started segments of `seg` consecutive positions: control flow of k_map / k_models"""
+        def strip(s, q, rho, G, zeta, seg, quadratic=0):
+            """warm-started segments of `seg` consecutive positions: control flow of k_map (two levels of
+            root history) / k_models (quadratic=1: three levels)"""
+            lib.emu_set_quadratic(quadratic)
             zeta = np.ascontiguousarray(zeta, dtype=np.complex128)
             n = zeta.size
             A = [np.zeros(n) for _ in range(3)]
@@ -253,7 +255,7 @@ def test_logic_warm_started_tracking_equals_cold_solves(emu):
         y = -half + (np.arange(nx // 4, 3 * nx // 4) + 0.5) * dy          # central half of the column
         for c in rng.integers(0, nx, 3):
             x = (cx - half + (c + 0.5) * dy) - s * q / (1 + q)
-            cases.append((s, q, 1e-3, x + 1j * y, 64))
+            cases.append((s, q, 1e-3, x + 1j * y, 64, 0))
     M = 40
     sv = np.exp(rng.uniform(np.log(0.5), np.log(2.), M))
     qv = np.exp(rng.uniform(np.log(1e-4), np.log(1.), M))
@@ -261,9 +263,9 @@ def test_logic_warm_started_tracking_equals_cold_solves(emu):
     uv, av = rng.uniform(-.5, .5, M), rng.uniform(0, 2 * np.pi, M)
     for m in range(M):
         T, seg = ((2000, 32) if m % 2 else (400, 7))
-        cases.append((sv[m], qv[m], rv[m], lightcurve_coordinates(sv[m], qv[m], uv[m], av[m], -2.0, 4.0 / T, T), seg))
-    for (s, q, rho, zeta, seg) in cases:
-        ni, A, fl, nc = emu.strip(s, q, rho, 0.5, zeta, seg)
+        cases.append((sv[m], qv[m], rv[m], lightcurve_coordinates(sv[m], qv[m], uv[m], av[m], -2.0, 4.0 / T, T), seg, 1))
+    for (s, q, rho, zeta, seg, quad) in cases:
+        ni, A, fl, nc = emu.strip(s, q, rho, 0.5, zeta, seg, quad)
         n0, B, f0 = emu.points(s, q, rho, 0.5, zeta)
         assert np.array_equal(ni, n0), (s, q, np.where(ni != n0)[0][:5])
         ok = (fl == 0) & (f0 == 0)

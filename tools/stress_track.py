@@ -10,7 +10,8 @@ from microlensing_b200.batched import lightcurve_coordinates
 ce.lib = ct.libs
 
 
-def run(M=200, T=2000, L=32, seed=1, qlo=1e-4):
+def run(M=200, T=2000, L=32, seed=1, qlo=1e-4, quadratic=1):
+    ct.libs.emu_set_quadratic(quadratic)      # k_models keeps three levels of root history
     rng = np.random.default_rng(seed)
     s = np.exp(rng.uniform(np.log(0.5), np.log(2.), M))
     q = np.exp(rng.uniform(np.log(qlo), np.log(1.), M))
