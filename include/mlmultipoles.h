@@ -73,6 +73,9 @@ int mlm_device_free(mlm_context* ctx, void* p);
 int mlm_ipc_export(mlm_context* ctx, void* p, unsigned char* handle /* [MLM_IPC_HANDLE_BYTES] */);
 int mlm_ipc_open(mlm_context* ctx, const unsigned char* handle, void** out);
 int mlm_ipc_close(mlm_context* ctx, void* p);
+/* cudaMemcpyAsync(cudaMemcpyDefault) on `stream`: bulk copy of a contiguous result block into a
+ * peer-mapped buffer (model grids, whose kernel stores are strided and would cross NVLink 8 bytes at a time). */
+int mlm_memcpy_async(mlm_context* ctx, void* dst, const void* src, int64_t bytes, void* stream);
 
 /* rows per warm-start strip of mlm_map (default 64; env MLM_MAP_STRIP at mlm_create) */
 int mlm_map_strip(mlm_context* ctx);

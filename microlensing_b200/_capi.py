@@ -34,6 +34,7 @@ SIGNATURES = {
     "mlm_ipc_export": [_P, _P, ctypes.c_char_p],
     "mlm_ipc_open": [_P, ctypes.c_char_p, ctypes.POINTER(_P)],
     "mlm_ipc_close": [_P, _P],
+    "mlm_memcpy_async": [_P, _P, _P, _L, _P],
     "mlm_points": [_P, _D, _D, _D, _D, _P, _L, _I, _P, _P, _P, _P, _P, _P],
     "mlm_points_host": [_P, _D, _D, _D, _D, _P, _L, _I, _P, _P, _P, _P, _P],
     "mlm_map": [_P, _D, _D, _D, _D, _D, _D, _D, _D, _L, _L, _L, _I, _P, _P, _P, _P, _P, _P],
@@ -157,6 +158,9 @@ class Context:
         p = _P()
         self.check(self.lib.mlm_ipc_open(self.handle, ctypes.c_char_p(handle), ctypes.byref(p)), "mlm_ipc_open")
         return int(p.value)
+
+    def memcpy_async(self, dst: int, src: int, nbytes: int, stream: int | None):
+        self.check(self.lib.mlm_memcpy_async(self.handle, _P(dst), _P(src), int(nbytes), _P(stream)), "mlm_memcpy_async")
 
     def ipc_close(self, p: int):
         self.check(self.lib.mlm_ipc_close(self.handle, _P(p)), "mlm_ipc_close")

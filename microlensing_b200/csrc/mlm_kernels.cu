@@ -602,6 +602,14 @@ int mlm_ipc_open(mlm_context* ctx, const unsigned char* handle, void** out) {
     return 0;
 }
 
+int mlm_memcpy_async(mlm_context* ctx, void* dst, const void* src, int64_t bytes, void* stream) {
+    if (!ctx || bytes < 0 || (bytes > 0 && (!dst || !src))) return fail(ctx, MLM_EINVAL, "mlm_memcpy_async: bad argument");
+    if (bytes == 0) return 0;
+    DeviceGuard g(ctx->device);
+    CK(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, pick(ctx, stream)));   // UVA: peer-mapped dst ok
+    return 0;
+}
+
 int mlm_ipc_close(mlm_context* ctx, void* p) {
     if (!ctx) return fail(ctx, MLM_EINVAL, "mlm_ipc_close: NULL context");
     if (!p) return 0;

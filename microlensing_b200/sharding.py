@@ -323,8 +323,10 @@ class ShardedModels:
     """Model grid (M models x T epochs of a straight trajectory) sharded by contiguous model ranges over
     the ranks (BASELINE.json configs[4]), results on rank 0.
 
-    fit=None : the M x T magnifications (26 B per epoch, or the `outputs` subset) are written by every
-               rank's kernel straight into rank 0's buffer (same fused peer-store gather as ShardedMap).
+    fit=None : the M x T magnifications (26 B per epoch, or the `outputs` subset) reach rank 0's buffer as
+               bulk peer copies of each rank's contiguous model block, chunk-pipelined behind the kernels
+               (the light-curve kernel's stores are strided by the segment length: sent over NVLink
+               directly they would travel 8 bytes at a time -- measured 2x SLOWER at 8 GPUs than 1).
     fit=(flux, sigma): the light-curve fit is fused into the kernel (mlm_models_chi2); only 8 doubles per
                model travel.
     A model's light curve does not depend on which rank computes it (the segment length of the kernel
@@ -384,6 +386,16 @@ class ShardedModels:
                 self.full = {key: raw[layout[key]: layout[key] + n * item].view(torch.float64 if item == 8 else torch.uint8)
                              .view(self.M, self.T) for key, item in KEYS}
         self._fence = torch.zeros(1, dtype=torch.float32, device=self.device) if world > 1 else None
+        # ranks > 0 compute into a local block and push it to rank 0 in `nchunks` bulk copies
+        self.local = None
+        self.comm_stream = None
+        if rank != 0 and self.fit is None and self.hi > self.lo:
+            n = (self.hi - self.lo) * self.T
+            self.local = {key: torch.empty(n, dtype=torch.float64 if item == 8 else torch.uint8, device=self.device)
+                          for key, item in KEYS if key in self.outputs}
+            with torch.cuda.device(self.device):
+                self.comm_stream = torch.cuda.Stream()
+        self.nchunks = 4
 
     def compute(self, order=4):
         """Enqueue this rank's models on the current stream (results land in rank 0's buffer)."""
@@ -396,11 +408,27 @@ class ShardedModels:
             if self.fit is not None:
                 models_chi2_device(*self.par, m, self.tau0, self.dtau, self.T, self.fit[0], self.fit[1],
                                    base + self.lo * 64, order=order, stream=st, device=self.device.index)
-            else:
+            elif self.local is None:
                 ptr = {key: (base + self.layout[key] + self.lo * self.T * item if key in self.outputs else None)
                        for key, item in KEYS}
                 models_device(*self.par, m, self.tau0, self.dtau, self.T, ptr["A0"], ptr["A2"], ptr["A4"], ptr["nimg"],
                               ptr["flags"], order=order, stream=st, device=self.device.index)
+            else:
+                cur = self.torch.cuda.current_stream(self.device)
+                for c in range(self.nchunks):
+                    a, b = shard_range(m, c, self.nchunks)
+                    if b == a:
+                        continue
+                    v = {key: (self.local[key][a * self.T:] if key in self.local else None) for key, _ in KEYS}
+                    models_device(*[p[a:b] for p in self.par], b - a, self.tau0, self.dtau, self.T, v["A0"], v["A2"],
+                                  v["A4"], v["nimg"], v["flags"], order=order, stream=st, device=self.device.index)
+                    self.comm_stream.wait_stream(cur)
+                    for key, item in KEYS:
+                        if key in self.local:
+                            ctx.memcpy_async(base + self.layout[key] + (self.lo + a) * self.T * item,
+                                             self.local[key].data_ptr() + a * self.T * item, (b - a) * self.T * item,
+                                             self.comm_stream.cuda_stream)
+                cur.wait_stream(self.comm_stream)
         if self.world > 1:
             dist.all_reduce(self._fence, group=self.group)          # stream-ordered completion fence
 
