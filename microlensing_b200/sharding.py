@@ -146,9 +146,16 @@ class ShardedMap:
         self.full = None
         self.comm_stream = None
         self._ipc = None
-        if gather == "p2p" and world > 1:
-            self._setup_p2p()
-        else:
+        if gather == "p2p" and world > 1 and not self._setup_p2p():
+            # peer mapping is not available on this box (no NVLink / IPC refused): every rank agreed to
+            # fall back to the NCCL gather with contiguous blocks
+            import warnings
+            warnings.warn("ShardedMap: CUDA IPC peer mapping failed, falling back to gather='nccl'")
+            gather = self.gather = "nccl"
+            self.layout = "block"
+            self.plan = plan_map(ny, rank, world, 4, align)
+            n_slot = self.n_slot = self.plan.max_rows * nx
+        if not (gather == "p2p" and world > 1):
             self.local = self._alloc(n_slot)
             if world > 1 and self.on_cuda:
                 with torch.cuda.device(self.device):
@@ -169,13 +176,29 @@ class ShardedMap:
         t, p = self.torch, self.plan
         ctx = _capi.context(self.device.index)
         layout, nbytes = full_map_layout(self.nx, self.ny)
-        box = [None]
-        if p.rank == 0:
-            base = ctx.device_alloc(nbytes)
-            box[0] = ctx.ipc_export(base)
+        box, base, err = [None], None, None
+        import os
+        if os.environ.get("MLM_DISABLE_IPC"):          # test hook: behave like a box without peer mapping
+            err = RuntimeError("MLM_DISABLE_IPC")
+        try:
+            if p.rank == 0 and err is None:
+                base = ctx.device_alloc(nbytes)
+                box[0] = ctx.ipc_export(base)
+        except Exception as e:            # noqa: BLE001 -- reported collectively below
+            err = e
         dist.broadcast_object_list(box, src=0, group=self.group)
-        if p.rank != 0:
-            base = ctx.ipc_open(box[0])
+        if p.rank != 0 and box[0] is not None:
+            try:
+                base = ctx.ipc_open(box[0])
+            except Exception as e:        # noqa: BLE001
+                err = e
+        # the outcome is collective: either every rank has the mapping or none uses it
+        okf = t.tensor([0.0 if (err is not None or base is None) else 1.0], device=self.device)
+        dist.all_reduce(okf, op=dist.ReduceOp.MIN, group=self.group)
+        if float(okf[0]) < 1.0:
+            if base is not None:
+                (ctx.device_free if p.rank == 0 else ctx.ipc_close)(base)
+            return False
         self._ipc = (ctx, base, p.rank == 0)
         n = self.nx * self.ny
         lo = p.row0 * self.nx if self.layout == "block" else 0
@@ -189,6 +212,7 @@ class ShardedMap:
             self.full_map = {key: raw[layout[key]: layout[key] + n * item].view(t.float64 if item == 8 else t.uint8)
                              for key, item in KEYS}
         self._fence = t.zeros(1, dtype=t.float32, device=self.device)
+        return True
 
     def close(self):
         """Release the shared buffer (collective: every rank unmaps before rank 0 frees)."""

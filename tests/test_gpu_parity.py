@@ -411,6 +411,9 @@ def _two_gpu_worker(rank, world, port, gather, layout, out_dir):
     import torch
     import torch.distributed as dist
     os.environ["MLM_DEVICE"] = str(rank)
+    if layout == "fallback":                       # p2p requested, peer mapping "unavailable" -> NCCL gather
+        os.environ["MLM_DISABLE_IPC"] = "1"
+        layout = None
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
                             device_id=torch.device("cuda", rank))
@@ -419,20 +422,22 @@ def _two_gpu_worker(rank, world, port, gather, layout, out_dir):
         s, q, rho, G = 1.0, 0.5, 1e-3, 0.5
         nx, ny = 512, 320
         x0, y0, dx, dy = -0.88, -0.8, 1.6 / nx, 1.6 / ny
-        sm = ShardedMap(nx, ny, rank, world, gather=gather, layout=layout)
+        sm = ShardedMap(nx, ny, rank, world, gather=gather, layout=layout, align=8)
+        if os.environ.get("MLM_DISABLE_IPC"):
+            assert sm.gather == "nccl" and sm.layout == "block"
         for _ in range(2):
             sm.compute(s, q, rho, G, x0, y0, dx, dy)
         torch.cuda.synchronize()
         full = sm.assemble_host()
         if rank == 0:
-            np.savez(os.path.join(out_dir, f"full_{gather}_{layout}.npz"), **full)
+            np.savez(os.path.join(out_dir, "full.npz"), **full)
         dist.barrier()
         sm.close()
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("gather,layout", [("p2p", "cyclic"), ("p2p", "block"), ("nccl", "block")])
+@pytest.mark.parametrize("gather,layout", [("p2p", "cyclic"), ("p2p", "block"), ("nccl", "block"), ("p2p", "fallback")])
 def test_two_gpu_sharded_map_equals_single_gpu(mb, tmp_path, gather, layout):
     """Row-sharded over 2 GPUs with the fused peer-store gather (and the NCCL gather): rank 0's
     assembled map is bit-identical to the single-GPU map."""
@@ -445,7 +450,7 @@ def test_two_gpu_sharded_map_equals_single_gpu(mb, tmp_path, gather, layout):
         sk.bind(("127.0.0.1", 0))
         port = sk.getsockname()[1]
     mp.spawn(_two_gpu_worker, args=(2, port, gather, layout, str(tmp_path)), nprocs=2, join=True)
-    got = np.load(tmp_path / f"full_{gather}_{layout}.npz")
+    got = np.load(tmp_path / "full.npz")
     s, q, rho, G = 1.0, 0.5, 1e-3, 0.5
     nx, ny = 512, 320
     # the single-GPU map with the strip length the sharded run picked (auto_strip) is bit-identical;
@@ -454,7 +459,8 @@ def test_two_gpu_sharded_map_equals_single_gpu(mb, tmp_path, gather, layout):
     ctx = mb._capi.context()
     default = mb.magnification_map(s, q, rho, G, -0.88, -0.8, 1.6 / nx, 1.6 / ny, nx, ny)
     old = ctx.map_strip()
-    ctx.set_map_strip(auto_strip(nx, ny // 2))
+    assert auto_strip(nx, ny // 2) == 8              # what the workers pinned with align=8
+    ctx.set_map_strip(8)
     try:
         one = mb.magnification_map(s, q, rho, G, -0.88, -0.8, 1.6 / nx, 1.6 / ny, nx, ny)
     finally:
