@@ -496,6 +496,27 @@ def other_configs(mb, dev, reps=3):
         ms = e0.elapsed_time(e1) / reps
         out[label] = dict(positions=n, ms=ms, mags_per_s=n / (ms * 1e-3), **(extra or {}))
 
+    # C1: the drop-in functions on the example() case (single position, 5 images): wall-clock latency per call
+    from microlensing_b200.multipoles import multipoles as mp
+    s1, q1, rho1, G1 = 1.7, 0.2, 0.01, 0.0
+    zeta0 = complex(-.5, 0.) - complex(s1 * q1 / (1. + q1), 0.)
+    z0 = mp._solvelenseq(s1, q1, zeta0)
+    Wk = np.zeros((7, 5), dtype=np.complex128)
+    for k in range(2, 7):
+        Wk[k] = (-1) ** (k - 1) * float(np.prod(np.arange(1, k))) / (1 + q1) * (z0 ** -k + q1 * (z0 + s1) ** -k)
+    lat = {}
+    for name, fn in (("_solvelenseq", lambda: mp._solvelenseq(s1, q1, zeta0)),
+                     ("hexadecapole(Wk)", lambda: mp.hexadecapole(Wk, rho1, G1)),
+                     ("magnification_points(1 position)", lambda: mb.magnification_points(s1, q1, rho1, G1, zeta0))):
+        for _ in range(20):
+            fn()
+        t0 = time.perf_counter()
+        for _ in range(300):
+            fn()
+        lat[name] = (time.perf_counter() - t0) / 300 * 1e6
+    out["C1_dropin_latency_us_per_call"] = dict(lat, note="host call -> H2D -> kernel(s) -> D2H -> return, one position; "
+                                                "the reference needs ~450 us for the same position on one core")
+
     c = CONFIGS["C3"]
     x0, y0, dx, dy = map_window(c)
     n = c["nx"] * c["ny"]

@@ -674,16 +674,246 @@ MLM_HD void accumulate_images(const LensTable& T, const SourceFactors sf, cd zet
     out.A0 = A0; out.A2 = A2; out.A4 = A4; out.nimg = n; out.flags = flags;
 }
 
+// =======================================================================================
+// Image-tracking path (k_map, k_models, k_points).
+//
+// Along a coherent sequence of source positions the PHYSICAL images are carried from one position to
+// the next by Newton on the lens equation itself (well conditioned, and its converged iterate IS
+// the polished image: no separate residual test, no polish), the non-physical roots by Newton on
+// the quintic (they are watched only for the moment they turn physical).  The roots are kept
+// sorted, physical images first, so that "k < nimg" is the image test.  A position whose tracking
+// is rejected (an iteration that does not contract, or five results that are not five distinct
+// roots: Vieta) is re-solved cold and re-classified with the reference's residual test.
+// =======================================================================================
+
+// One Newton iteration on f(z) = z - zeta - conj(W1(z)):  dz = -(f + conj(W2) conj(f)) / (1 - |W2|^2).
+// d2 = squared distance of z to the nearer lens (the scale on which the images live).
+MLM_HD cd lens_newton(const LensTable& T, cd zeta, cd z, double& dz2, double& d2, double& z2) {
+    const cd zs = mk(z.x + T.s, z.y);
+    z2 = norm2(z);
+    const double zs2 = norm2(zs);
+    d2 = fmin(z2, zs2);
+    const double i1 = rcp(z2), i2 = rcp(zs2);
+    const cd r1 = mk(z.x * i1, -(z.y * i1)), r2 = mk(zs.x * i2, -(zs.y * i2));
+    const cd W1 = rfma(T.alpha[1], r1, scale(T.beta[1], r2));
+    const cd f = z - zeta - conj(W1);
+    const cd W2 = rfma(T.alpha[2], csq(r1), scale(T.beta[2], csq(r2)));
+    const double iJ = rcp_step(1.0 - norm2(W2));
+    const cd dz = scale(-iJ, cjfma(W2, conj(f), f));
+    dz2 = norm2(dz);
+    return z + dz;
+}
+
+// Classification of a fresh set of polynomial roots (cold solve, or a non-physical root that came
+// close to the lens equation): the reference's residual test |z - conj(W1) - zeta| < 1e-6
+// (multipoles.py:182-183; NaN -> rejected, like NumPy), the accepted images polished by Newton on the
+// lens equation, roots with a residual in (1e-6, 1e-1) rescued iff that Newton, started with a step
+// < 1e-7, converges (root noise of the ill-conditioned quintic at small q, amplified by |W2| up to
+// 1e7).  Afterwards the store holds the physical images first (original order kept within each group).
+// Returns the number of physical images.
+MLM_HD int classify_roots(const LensTable& T, cd zeta, cd* sz, int stride, unsigned& flags) {
+    unsigned phys_mask = 0;
+    cd zk5[5];
+#pragma unroll 1
+    for (int k = 0; k < 5; ++k) {
+        cd zk = sz[k * stride];
+        cd zs = mk(zk.x + T.s, zk.y);
+        cd r1 = crcp(zk), r2 = crcp(zs);
+        cd W1 = rfma(T.alpha[1], r1, scale(T.beta[1], r2));
+        cd f = zk - zeta - conj(W1);
+        const double f2 = norm2(f);
+        if (f2 > 1e-14 && f2 < 1e-10) flags |= MLM_FLAG_AMBIG;
+        if (!(f2 < 1e-2)) continue;
+        bool phys = (f2 < 1e-12);                     // the reference's test, multipoles.py:183
+        bool conv = false;
+        double lim = phys ? 1e-10 : 1e-14;
+#pragma unroll 1
+        for (int it = 0; it < 3; ++it) {
+            const cd W2 = rfma(T.alpha[2], csq(r1), scale(T.beta[2], csq(r2)));
+            const double iJ = rcp_step(1.0 - norm2(W2));
+            const cd dz = scale(-iJ, cjfma(W2, conj(f), f));
+            const double dz2 = norm2(dz);
+            // (8 ulp of |z|)^2: steps at the rounding level of z count as converged, not as stalled
+            const double ulp2 = 3.2e-30 * norm2(zk);
+            if (!(dz2 < fmax(lim, ulp2))) break;
+            zk = zk + dz;
+            zs = mk(zk.x + T.s, zk.y);
+            r1 = crcp(zk);
+            r2 = crcp(zs);
+            if (dz2 <= fmax(1e-20 * fmin(norm2(zk), norm2(zs)), ulp2)) { conv = true; break; }
+            lim = 1e-4 * dz2;
+            W1 = rfma(T.alpha[1], r1, scale(T.beta[1], r2));
+            f = zk - zeta - conj(W1);
+        }
+        if (!phys) phys = conv;
+        if (phys) {
+            phys_mask |= 1u << k;
+            sz[k * stride] = zk;                      // the polished image
+        }
+    }
+    // stable partition: physical images first
+#pragma unroll
+    for (int k = 0; k < 5; ++k) zk5[k] = sz[k * stride];
+    int w = 0;
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+        if ((phys_mask >> k) & 1u) sz[(w++) * stride] = zk5[k];
+    const int nimg = w;
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+        if (!((phys_mask >> k) & 1u)) sz[(w++) * stride] = zk5[k];
+    return nimg;
+}
+
+// Tracking state of a thread along its sequence (registers).
+struct TrackState {
+    int hist;      // usable earlier positions: 0 cold start, 1 previous roots, 2 linear, 3 quadratic extrapolation
+    int nimg;      // physical images = the first nimg entries of the root store
+};
+
+// One step of a coherent sequence: bring the root store (sz current, szp previous, szpp -- optional --
+// the one before; [k * stride], shared memory in the kernels) to the source position zeta with
+// polynomial c.  `ratio` = (this source step) / (previous one) for unevenly spaced sequences.
+MLM_HD void advance_images(const LensTable& T, cd zeta, const cd c[6], cd* sz, cd* szp, cd* szpp, int stride,
+                           TrackState& st, unsigned& flags, double ratio = 1.0) {
+    bool need_cold = true, need_classify = false;
+    cd z[5];
+    if (st.hist >= 1 && !(c[5].x == 0.0 && c[5].y == 0.0)) {
+        // start values: previous roots, linear (2 z1 - z2) or quadratic (3 z1 - 3 z2 + z3) extrapolation
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const cd zc = sz[k * stride];
+            cd pred = zc;
+            if (st.hist >= 2) {
+                const cd zo = szp[k * stride];
+                if (ratio == 1.0) {
+                    if (szpp != nullptr && st.hist >= 3) {
+                        const cd zoo = szpp[k * stride];
+                        pred = mk(fma(3.0, zc.x - zo.x, zoo.x), fma(3.0, zc.y - zo.y, zoo.y));
+                    } else {
+                        pred = mk(fma(2.0, zc.x, -zo.x), fma(2.0, zc.y, -zo.y));
+                    }
+                } else {
+                    pred = mk(fma(ratio, zc.x - zo.x, zc.x), fma(ratio, zc.y - zo.y, zc.y));
+                }
+                if (szpp != nullptr) szpp[k * stride] = zo;
+            }
+            szp[k * stride] = zc;
+            z[k] = pred;
+        }
+        bool ok = true;
+        cd sum = mk(0.0, 0.0);
+        double mag = 1.0;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            cd zk = z[k];
+            bool conv = false;
+            if (k < st.nimg) {
+                // physical image: Newton on the lens equation.  A step below 1e-7 d leaves an error of
+                // ~ (1e-7 d)^2 / d = 1e-14 d: done; every further step must contract by >= 10.
+                double lim = 1e300;
+#pragma unroll 1
+                for (int it = 0; it < 4; ++it) {
+                    double dz2, d2, z2;
+                    const cd zn = lens_newton(T, zeta, zk, dz2, d2, z2);
+                    MLM_COUNT(lens_evals);
+                    if (!(dz2 < lim)) break;
+                    zk = zn;
+                    if (dz2 <= fmax(1e-14 * d2, 3.2e-30 * z2)) { conv = true; break; }
+                    lim = 1e-2 * dz2;
+                }
+            } else {
+                // non-physical root: Newton on the quintic, then a look at its lens-equation residual
+                double prev = 1e300;
+#pragma unroll 1
+                for (int j = 0; j < 6; ++j) {
+                    double dz2;
+                    zk = newton_step(c, zk, dz2);
+                    if (newton_stop(dz2, prev, zk, T.s)) { conv = true; break; }
+                    prev = 0.25 * dz2;
+                }
+                const cd zs = mk(zk.x + T.s, zk.y);
+                const cd W1 = rfma(T.alpha[1], crcp(zk), scale(T.beta[1], crcp(zs)));
+                const double f2 = norm2(zk - zeta - conj(W1));
+                if (f2 < 1e-2) need_classify = true;  // it may have turned physical (caustic crossing)
+            }
+            ok = ok && conv;
+            z[k] = zk;
+            sum = sum + zk;
+            mag += norm2(zk);
+        }
+        // five DISTINCT roots?  (Vieta: sum z_k = -c4/c5; two tracks on one root break it by their separation)
+        const cd v = cfma(c[4], crcp(c[5]), sum);
+        if (ok && norm2(v) <= 1e-16 * mag) {
+#pragma unroll
+            for (int k = 0; k < 5; ++k) sz[k * stride] = z[k];
+            need_cold = false;
+            st.hist = (szpp != nullptr && st.hist >= 2) ? 3 : 2;
+        } else {
+            MLM_COUNT(track_fallbacks);
+        }
+    }
+    if (need_cold) {
+        const int deg = solve_roots(c, T.s, z, flags);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) sz[k * stride] = z[k];
+        need_classify = true;
+        st.hist = (deg == 5) ? 1 : 0;
+    }
+    if (need_classify) {
+        st.nimg = classify_roots(T, zeta, sz, stride, flags);
+        if (st.hist > 1) st.hist = 1;                 // the order of the store changed: history is void
+    }
+}
+
+// A0, A2, A4 of a position from its images (the first nimg entries of the root store):
+// W_k (multipoles.py:197-201), mu0/mu2/mu4 per image, sums of |...| (multipoles.py:144-146).
+template <int ORDER>
+MLM_HD void sum_images(const LensTable& T, const SourceFactors sf, const cd* sz, int stride, int nimg,
+                       PointResult& out) {
+    double A0 = 0.0, A2 = 0.0, A4 = 0.0, minJ = 1e300;
+    unsigned flags = out.flags;
+#pragma unroll 1
+    for (int k = 0; k < nimg; ++k) {
+        const cd zk = sz[k * stride];
+        const cd zs = mk(zk.x + T.s, zk.y);
+        const cd r1 = crcp(zk), r2 = crcp(zs);
+        const cd a2 = csq(r1), b2 = csq(r2);
+        const cd a3 = cmul(a2, r1), b3 = cmul(b2, r2);
+        const cd a4 = csq(a2), b4 = csq(b2);
+        const cd W2 = rfma(T.alpha[2], a2, scale(T.beta[2], b2));
+        const cd W3 = rfma(T.alpha[3], a3, scale(T.beta[3], b3));
+        const cd W4 = rfma(T.alpha[4], a4, scale(T.beta[4], b4));
+        cd W5 = mk(0.0, 0.0), W6 = mk(0.0, 0.0);
+        if (ORDER >= 4) {
+            const cd a5 = cmul(a4, r1), b5 = cmul(b4, r2);
+            const cd a6 = csq(a3), b6 = csq(b3);
+            W5 = rfma(T.alpha[5], a5, scale(T.beta[5], b5));
+            W6 = rfma(T.alpha[6], a6, scale(T.beta[6], b6));
+        }
+        const ImageTerms t = image_terms_from_W<ORDER>(W2, W3, W4, W5, W6);
+        const double v2 = fma(sf.h2, t.mu2, t.mu0);
+        A0 += fabs(t.mu0);
+        A2 += fabs(v2);
+        if (ORDER >= 4) A4 += fabs(fma(sf.h4, t.mu4, v2));
+        minJ = fmin(minJ, fabs(1.0 - norm2(W2)));
+    }
+    if (minJ < 1e-3) flags |= MLM_FLAG_NEARCRIT;
+    if (ORDER >= 4 && fabs(A4 - A2) > fabs(A2 - A0)) flags |= MLM_FLAG_SERIES;
+    out.A0 = A0; out.A2 = A2; out.A4 = A4; out.nimg = (unsigned)nimg; out.flags = flags;
+}
+
 // whole path for one source position (cold start)
 template <int ORDER>
 MLM_HD PointResult point_magnification(const LensTable& T, const SourceFactors sf, cd zeta) {
     cd c[6], z[5];
     PointResult out;
     out.flags = 0;
+    TrackState st;
+    st.hist = 0; st.nimg = 0;
     lens_polynomial(T, zeta, c);
-    cd scratch[10];
-    solve_roots(c, T.s, z, out.flags);
-    accumulate_images<ORDER>(T, sf, zeta, z, 1, scratch, 1, out);
+    advance_images(T, zeta, c, z, z, nullptr, 1, st, out.flags);
+    sum_images<ORDER>(T, sf, z, 1, st.nimg, out);
     return out;
 }
 

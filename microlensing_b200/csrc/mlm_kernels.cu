@@ -55,13 +55,13 @@ k_points(const __grid_constant__ LensTable T, const SourceFactors sf, const doub
          int seg, double* __restrict__ A0, double* __restrict__ A2, double* __restrict__ A4,
          uint8_t* __restrict__ nimg, uint8_t* __restrict__ flags) {
     __shared__ cd s_roots[2][5][MLM_BLOCK];
-    __shared__ cd s_rcp[10][MLM_BLOCK];
     cd* const sz = &s_roots[0][0][threadIdx.x];
     cd* const szp = &s_roots[1][0][threadIdx.x];
     const int64_t i0 = ((int64_t)blockIdx.x * MLM_BLOCK + threadIdx.x) * seg;
     if (i0 >= n) return;
     const int64_t i1 = (i0 + seg < n) ? i0 + seg : n;
-    int hist = 0;
+    TrackState st;
+    st.hist = 0; st.nimg = 0;
     cd zprev = mk(0.0, 0.0), dprev = mk(0.0, 0.0);
     for (int64_t i = i0; i < i1; ++i) {
         const double2 zz = __ldg(zeta + i);
@@ -69,18 +69,18 @@ k_points(const __grid_constant__ LensTable T, const SourceFactors sf, const doub
         const cd d = zt - zprev;
         const double d2 = norm2(d);
         double ratio = 1.0;
-        if (hist >= 1 && !(d2 <= 1e-2)) hist = 0;                 // jump (or NaN): start afresh
-        if (hist >= 2) {
+        if (st.hist >= 1 && !(d2 <= 1e-2)) st.hist = 0;           // jump (or NaN): start afresh
+        if (st.hist >= 2) {
             // projection of this step on the previous one; a sensible extrapolation only for 0 < ratio < 4
             ratio = re_mulc(d, dprev) * rcp(norm2(dprev));
-            if (!(ratio > 0.0 && ratio < 4.0)) hist = 1;
+            if (!(ratio > 0.0 && ratio < 4.0)) st.hist = 1;
         }
         cd c[6];
         PointResult r;
         r.flags = 0;
         lens_polynomial(T, zt, c);
-        hist = advance_roots(c, T.s, sz, szp, MLM_BLOCK, hist, r.flags, ratio);
-        accumulate_images<ORDER>(T, sf, zt, sz, MLM_BLOCK, &s_rcp[0][threadIdx.x], MLM_BLOCK, r);
+        advance_images(T, zt, c, sz, szp, nullptr, MLM_BLOCK, st, r.flags, ratio);
+        sum_images<ORDER>(T, sf, sz, MLM_BLOCK, st.nimg, r);
         store_result(r, i, A0, A2, A4, nimg, flags);
         zprev = zt;
         dprev = d;
@@ -102,10 +102,10 @@ k_map(const __grid_constant__ LensTable T, const SourceFactors sf, double x0, do
       double* __restrict__ A2, double* __restrict__ A4, uint8_t* __restrict__ nimg, uint8_t* __restrict__ flags) {
     // root store of this thread: current and previous roots, [k][thread] so that a warp touches
     // 512 contiguous bytes per k (conflict-free); keeps 20 doubles out of the register file
-    __shared__ cd s_roots[2][5][MLM_BLOCK];
-    __shared__ cd s_rcp[10][MLM_BLOCK];                // 1/z, 1/(z+s) of the five roots (accumulate_images)
+    __shared__ cd s_roots[3][5][MLM_BLOCK];
     cd* const sz = &s_roots[0][0][threadIdx.x];
     cd* const szp = &s_roots[1][0][threadIdx.x];
+    cd* const szpp = &s_roots[2][0][threadIdx.x];
     const int64_t col = (int64_t)blockIdx.x * MLM_BLOCK + threadIdx.x;
     if (col >= nx) return;
     // x = x0 + (col + 0.5) dx with two roundings (no FMA), so that host code can reproduce
@@ -126,7 +126,8 @@ k_map(const __grid_constant__ LensTable T, const SourceFactors sf, double x0, do
         const int64_t k = kphase + (i_first + ii) * kstep;
         const int64_t ra = (k * strip > row0) ? k * strip : row0;
         const int64_t rb = ((k + 1) * strip < row0 + nrows) ? (k + 1) * strip : row0 + nrows;
-        int hist = 0;
+        TrackState st;
+        st.hist = 0; st.nimg = 0;
         for (int64_t r = ra; r < rb; ++r) {
             const double y = __dadd_rn(y0, __dmul_rn((double)r + 0.5, dy));
             const cd zeta = mk(x, y);
@@ -134,8 +135,8 @@ k_map(const __grid_constant__ LensTable T, const SourceFactors sf, double x0, do
             PointResult res;
             res.flags = 0;
             lens_polynomial(T, zeta, c);
-            hist = advance_roots(c, T.s, sz, szp, MLM_BLOCK, hist, res.flags);
-            accumulate_images<ORDER>(T, sf, zeta, sz, MLM_BLOCK, &s_rcp[0][threadIdx.x], MLM_BLOCK, res);
+            advance_images(T, zeta, c, sz, szp, szpp, MLM_BLOCK, st, res.flags);
+            sum_images<ORDER>(T, sf, sz, MLM_BLOCK, st.nimg, res);
             store_result(res, (r - row0) * nx + col, A0, A2, A4, nimg, flags);
         }
     }
@@ -158,7 +159,6 @@ k_models(const double* __restrict__ s, const double* __restrict__ q, const doubl
     __shared__ SourceFactors sf;
     __shared__ double rot[3];                          // cos(alpha), sin(alpha), shift
     __shared__ cd s_roots[3][5][MLM_MODELS_BLOCK];
-    __shared__ cd s_rcp[10][MLM_MODELS_BLOCK];
     cd* const sz = &s_roots[0][0][threadIdx.x];
     cd* const szp = &s_roots[1][0][threadIdx.x];
     cd* const szpp = &s_roots[2][0][threadIdx.x];
@@ -180,7 +180,8 @@ k_models(const double* __restrict__ s, const double* __restrict__ q, const doubl
              sg += (int64_t)gridDim.x * MLM_MODELS_BLOCK) {
             const int64_t t0 = sg * seg;
             const int64_t t1 = (t0 + seg < Tn) ? t0 + seg : Tn;
-            int hist = 0;
+            TrackState st;
+            st.hist = 0; st.nimg = 0;
             for (int64_t t = t0; t < t1; ++t) {
                 // compiler barrier: the table is re-read from shared memory where it is used instead of
                 // being hoisted out of the loop into ~40 live registers
@@ -194,8 +195,8 @@ k_models(const double* __restrict__ s, const double* __restrict__ q, const doubl
                 PointResult res;
                 res.flags = 0;
                 lens_polynomial(T, zeta, c);
-                hist = advance_roots(c, T.s, sz, szp, MLM_MODELS_BLOCK, hist, res.flags, 1.0, szpp);
-                accumulate_images<ORDER>(T, sf, zeta, sz, MLM_MODELS_BLOCK, &s_rcp[0][threadIdx.x], MLM_MODELS_BLOCK, res);
+                advance_images(T, zeta, c, sz, szp, szpp, MLM_MODELS_BLOCK, st, res.flags);
+                sum_images<ORDER>(T, sf, sz, MLM_MODELS_BLOCK, st.nimg, res);
                 store_result(res, m * Tn + t, A0, A2, A4, nimg, flags);
             }
         }
@@ -218,7 +219,6 @@ k_models_chi2(const double* __restrict__ s, const double* __restrict__ q, const 
     __shared__ SourceFactors sf;
     __shared__ double rot[3];
     __shared__ cd s_roots[3][5][MLM_MODELS_BLOCK];
-    __shared__ cd s_rcp[10][MLM_MODELS_BLOCK];
     __shared__ double s_red[8][MLM_MODELS_BLOCK];
     cd* const sz = &s_roots[0][0][threadIdx.x];
     cd* const szp = &s_roots[1][0][threadIdx.x];
@@ -241,7 +241,8 @@ k_models_chi2(const double* __restrict__ s, const double* __restrict__ q, const 
         for (int64_t sg = threadIdx.x; sg < nseg; sg += MLM_MODELS_BLOCK) {
             const int64_t t0 = sg * seg;
             const int64_t t1 = (t0 + seg < Tn) ? t0 + seg : Tn;
-            int hist = 0;
+            TrackState st;
+            st.hist = 0; st.nimg = 0;
             for (int64_t t = t0; t < t1; ++t) {
                 asm volatile("" ::: "memory");
                 const double tau = __dadd_rn(tau0, __dmul_rn((double)t, dtau));
@@ -252,8 +253,8 @@ k_models_chi2(const double* __restrict__ s, const double* __restrict__ q, const 
                 PointResult res;
                 res.flags = 0;
                 lens_polynomial(T, zeta, c);
-                hist = advance_roots(c, T.s, sz, szp, MLM_MODELS_BLOCK, hist, res.flags, 1.0, szpp);
-                accumulate_images<ORDER>(T, sf, zeta, sz, MLM_MODELS_BLOCK, &s_rcp[0][threadIdx.x], MLM_MODELS_BLOCK, res);
+                advance_images(T, zeta, c, sz, szp, szpp, MLM_MODELS_BLOCK, st, res.flags);
+                sum_images<ORDER>(T, sf, sz, MLM_MODELS_BLOCK, st.nimg, res);
                 const double A = (ORDER >= 4) ? res.A4 : res.A2;
                 const double w = __ldg(weight + t), f = __ldg(flux + t);
                 const double wa = w * A;

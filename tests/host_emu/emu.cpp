@@ -2,7 +2,7 @@
 // Lets the CPU test-suite check the kernel LOGIC (root finder, selection, Wirtinger
 // recursion) against the oracle without a GPU.  Never loaded by microlensing_b200.
 #ifdef MLM_STATS
-static long g_cnt_laguerre_evals = 0, g_cnt_newton_evals = 0, g_cnt_track_fallbacks = 0;
+static long g_cnt_laguerre_evals = 0, g_cnt_newton_evals = 0, g_cnt_track_fallbacks = 0, g_cnt_lens_evals = 0;
 #define MLM_COUNT(name) (++g_cnt_##name)
 #endif
 #include "../../microlensing_b200/csrc/mlm_core.cuh"
@@ -12,7 +12,7 @@ using namespace mlm;
 
 extern "C" {
 #ifdef MLM_STATS
-void emu_stats(long* out, int reset) { out[0] = g_cnt_laguerre_evals; out[1] = g_cnt_newton_evals; if (reset) g_cnt_laguerre_evals = g_cnt_newton_evals = 0; }
+void emu_stats(long* out, int reset) { out[0] = g_cnt_laguerre_evals; out[1] = g_cnt_newton_evals; out[2] = g_cnt_lens_evals; out[3] = g_cnt_track_fallbacks; if (reset) g_cnt_laguerre_evals = g_cnt_newton_evals = g_cnt_lens_evals = g_cnt_track_fallbacks = 0; }
 #endif
 
 
@@ -74,20 +74,20 @@ extern "C" void emu_strip(double s, double q, double rho, double Gamma, const do
     make_table(s, q, &T);
     SourceFactors sf = source_factors(rho, Gamma);
     cd z[5], zp[5], zpp[5];
-    int hist = 0;
+    TrackState st;
+    st.hist = 0; st.nimg = 0;
     long cold = 0;
     for (long i = 0; i < n; ++i) {
-        if (i % strip == 0) hist = 0;
+        if (i % strip == 0) st.hist = 0;
         cd zeta_i = mk(zeta[2 * i], zeta[2 * i + 1]);
         cd c[6];
         PointResult r;
         r.flags = 0;
         lens_polynomial(T, zeta_i, c);
-        const int before = hist;
-        hist = advance_roots(c, T.s, z, zp, 1, hist, r.flags, 1.0, g_quadratic ? zpp : nullptr);
-        if (before == 0 || hist < 2) ++cold;
-        cd scratch[10];
-        accumulate_images<4>(T, sf, zeta_i, z, 1, scratch, 1, r);
+        const int before = st.hist;
+        advance_images(T, zeta_i, c, z, zp, g_quadratic ? zpp : nullptr, 1, st, r.flags);
+        if (before == 0 || st.hist < 2) ++cold;
+        sum_images<4>(T, sf, z, 1, st.nimg, r);
         A0[i] = r.A0; A2[i] = r.A2; A4[i] = r.A4;
         nimg[i] = (unsigned char)r.nimg; flags[i] = (unsigned char)r.flags;
     }

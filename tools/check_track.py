@@ -13,7 +13,7 @@ def strip(s,q,rho,G,zeta,L):
     libs.emu_strip(ctypes.c_double(s),ctypes.c_double(q),ctypes.c_double(rho),ctypes.c_double(G),zeta.view(np.float64).ctypes.data_as(dp),ctypes.c_long(n),ctypes.c_int(L),*[a.ctypes.data_as(dp) for a in A],ni.ctypes.data_as(up),fl.ctypes.data_as(up),ctypes.byref(nc))
     return ni,np.stack(A,1),fl,nc.value
 def stats(reset=1):
-    st=np.zeros(2,np.int64); libs.emu_stats(st.ctypes.data_as(ctypes.POINTER(ctypes.c_long)),reset); return st
+    st=np.zeros(4,np.int64); libs.emu_stats(st.ctypes.data_as(ctypes.POINTER(ctypes.c_long)),reset); return st
 if __name__=="__main__":
   for name,s,q,cx,half,nx in (("C4",1.0,0.5,-0.08,0.8,8192),("C3",0.8,0.1,0.11,0.75,4096)):
     rng=np.random.default_rng(1)
@@ -43,3 +43,4 @@ if __name__=="__main__":
         strip(s,q,1e-3,0.5,x+1j*y,32); tot+=nx
     st=stats()
     print('tracked: laguerre evals/pt',st[0]/tot,'newton evals/pt',st[1]/tot)
+    print('       lens evals/pt', st[2]/tot, 'track fallbacks/pt', st[3]/tot)
