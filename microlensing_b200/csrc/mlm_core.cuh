@@ -1,11 +1,14 @@
 // mlm_core.cuh -- per-source-position arithmetic of the binary-lens A0/A2/A4 path.
 //
-// Everything here runs in registers of ONE thread (one source position):
+// Everything here runs in ONE thread (one source position; five roots of state in shared memory):
 //   (a) lens polynomial from (s, q, zeta)        reference: multipoles.py:159-164
 //   (b) all complex roots (Laguerre + deflation, Newton polish)   replaces np.roots, multipoles.py:165
 //   (c) physical images by the residual test     reference: multipoles.py:182-183
 //   (d) W_2..W_6 per image                        reference: multipoles.py:197-201
 //   (e) mu0, mu2, mu4 per image and the sums      reference: multipoles.py:91-146
+// Along a coherent sequence of positions (map column, light curve) (b)+(c) are replaced by TRACKING:
+// images follow Newton on the lens equation, non-physical roots Newton on the quintic, and a cold
+// (b)+(c) happens only at sequence starts and where tracking is rejected (advance_images).
 //
 // (e) is NOT a transcription of the reference's (xi, eta) recursion over 20 Taylor factors a_kl:
 // mu2 and mu4 are the source-plane Laplacian and bi-Laplacian of mu0, evaluated in closed form with
@@ -372,13 +375,7 @@ MLM_HD int solve_roots(const cd c[6], double s, cd z[5], unsigned& flags) {
     return deg0;
 }
 
-// Warm start: the five roots of a NEIGHBOURING source position (previous map row / previous
-// epoch) are carried into the new polynomial by Newton iterations on the full quintic, which
-// replaces the ~14 Laguerre iterations of the cold solve by ~3 Newton steps per root.
-// Returns false -- the caller then falls back to solve_roots() -- unless every iteration
-// converged and the five results are five DISTINCT roots (Vieta: sum z_k = -c4/c5; two tracks
-// collapsing onto one root, the failure mode next to a caustic, breaks the sum by their
-// separation).  The accepted roots satisfy the same stopping rule as the cold path's polish.
+// One Newton step on the quintic (used for the non-physical roots of the tracking path).
 MLM_HD cd newton_step(const cd c[6], cd zk, double& dz2) {
     cd p, dp;
     horner2(c, zk, p, dp);
@@ -388,92 +385,6 @@ MLM_HD cd newton_step(const cd c[6], cd zk, double& dz2) {
     const cd dz = scale(idp2, cmulc(dp, p));
     dz2 = norm2(dz);
     return zk - dz;
-}
-
-MLM_HD bool track_roots(const cd c[6], double s, cd z[5]) {
-    if (c[5].x == 0.0 && c[5].y == 0.0) return false;
-    // First Newton step of all five roots as straight-line code: five independent Horner chains
-    // that the scheduler interleaves (the per-root loops below are serial chains).  With the
-    // extrapolated start ~85 % of the roots are finished after this step.
-    double dz2[5];
-    bool conv[5];
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-        z[k] = newton_step(c, z[k], dz2[k]);
-        conv[k] = newton_stop(dz2[k], 1e300, z[k], s);
-    }
-    bool ok = true;
-    cd sum = mk(0.0, 0.0);
-    double mag = 1.0;
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-        if (!conv[k]) {
-            cd zk = z[k];
-            double prev = 0.25 * dz2[k];
-#pragma unroll 1
-            for (int j = 0; j < 5; ++j) {
-                double d2;
-                zk = newton_step(c, zk, d2);
-                if (newton_stop(d2, prev, zk, s)) { conv[k] = true; break; }
-                prev = 0.25 * d2;
-            }
-            z[k] = zk;
-        }
-        ok = ok && conv[k];
-        sum = sum + z[k];
-        mag += norm2(z[k]);
-    }
-    const cd v = cfma(c[4], crcp(c[5]), sum);
-    return ok && (norm2(v) <= 1e-16 * mag);
-}
-
-// One step of a coherent sequence of source positions (map column, light curve): bring the
-// root store (current roots sz[k*stride], previous roots szp[k*stride]; shared memory in the
-// kernels) to the new polynomial c.  hist = number of usable earlier positions (0: cold start,
-// 1: warm start from sz, 2: warm start from the linear extrapolation 2 sz - szp, which cuts the
-// initial error from O(h) to O(h^2) and the Newton work to ~1 step per root).  Falls back to
-// the cold solve whenever tracking is rejected.  Returns the new hist.
-// `ratio` = (this step of the source) / (previous step) for unevenly spaced sequences (1 on maps
-// and uniform light curves): the extrapolation is z + ratio (z - z_prev).
-// `szpp` (optional) = roots two positions back: with three equally spaced positions the start is the
-// quadratic extrapolation 3 z1 - 3 z2 + z3 (error O(h^3)), which keeps light curves sampled 10x
-// coarser than a map pixel at one Newton step per root.
-MLM_HD int advance_roots(const cd c[6], double s, cd* sz, cd* szp, int stride, int hist, unsigned& flags,
-                         double ratio = 1.0, cd* szpp = nullptr) {
-    cd z[5];
-    if (hist >= 1) {
-#pragma unroll
-        for (int k = 0; k < 5; ++k) {
-            const cd zc = sz[k * stride];
-            cd pred = zc;
-            if (hist >= 2) {
-                const cd zo = szp[k * stride];
-                if (ratio == 1.0) {
-                    if (szpp != nullptr && hist >= 3) {
-                        const cd zoo = szpp[k * stride];
-                        pred = mk(fma(3.0, zc.x - zo.x, zoo.x), fma(3.0, zc.y - zo.y, zoo.y));
-                    } else {
-                        pred = mk(fma(2.0, zc.x, -zo.x), fma(2.0, zc.y, -zo.y));
-                    }
-                } else {
-                    pred = mk(fma(ratio, zc.x - zo.x, zc.x), fma(ratio, zc.y - zo.y, zc.y));
-                }
-                if (szpp != nullptr) szpp[k * stride] = zo;
-            }
-            szp[k * stride] = zc;
-            z[k] = pred;
-        }
-        if (track_roots(c, s, z)) {
-#pragma unroll
-            for (int k = 0; k < 5; ++k) sz[k * stride] = z[k];
-            return (szpp != nullptr && hist >= 2) ? 3 : 2;
-        }
-        MLM_COUNT(track_fallbacks);
-    }
-    const int deg = solve_roots(c, s, z, flags);
-#pragma unroll
-    for (int k = 0; k < 5; ++k) sz[k * stride] = z[k];
-    return deg == 5 ? 1 : 0;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -572,107 +483,6 @@ struct PointResult {
     unsigned nimg;
     unsigned flags;
 };
-
-// (c)+(d)+(e): given the polynomial roots, select the physical images, polish them on the
-// lens equation itself, and accumulate A0/A2/A4.
-template <int ORDER>
-MLM_HD void accumulate_images(const LensTable& T, const SourceFactors sf, cd zeta, const cd* z, int zstride,
-                              cd* scratch, int sstride, PointResult& out) {
-    double A0 = 0.0, A2 = 0.0, A4 = 0.0, minJ = 1e300;
-    unsigned n = 0, flags = out.flags, cand = 0;
-    // Pass 1, straight-line over the five roots (five independent reciprocal chains in flight):
-    // residual of the lens equation, multipoles.py:182-183.  1/z and 1/(z+s) go to `scratch`
-    // ([2k], [2k+1] with stride sstride; shared memory in the kernels) for pass 2.
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-        const cd zk = z[k * zstride];
-        const cd zs = mk(zk.x + T.s, zk.y);
-        const cd r1 = crcp(zk), r2 = crcp(zs);
-        const cd W1 = rfma(T.alpha[1], r1, scale(T.beta[1], r2));
-        const cd f = zk - zeta - conj(W1);
-        const double f2 = norm2(f);
-        scratch[(2 * k) * sstride] = r1;
-        scratch[(2 * k + 1) * sstride] = r2;
-        if (f2 > 1e-14 && f2 < 1e-10) flags |= MLM_FLAG_AMBIG;
-        if (f2 < 1e-2) cand |= 1u << k;               // NaN residual -> rejected, like NumPy
-    }
-    // Pass 2, rolled over the candidates (5 x ~350 instructions would overflow the instruction
-    // cache).  Each lane walks ITS OWN candidate list (lowest set bit of `cand` first), so a warp runs
-    // max-over-lanes(#candidates) iterations even when the physical images sit at different root
-    // indices in different lanes (lanes of a light-curve kernel are far-apart epochs).  Roots and
-    // reciprocals are read back from memory with a per-lane index: no register array is indexed
-    // dynamically and they occupy no registers meanwhile.
-#pragma unroll 1
-    while (cand) {
-#if defined(__CUDA_ARCH__)
-        const int k = __ffs((int)cand) - 1;
-#else
-        const int k = __builtin_ctz(cand);
-#endif
-        cand &= cand - 1u;
-        cd zk = z[k * zstride];
-        cd zs = mk(zk.x + T.s, zk.y);
-        cd r1 = scratch[(2 * k) * sstride], r2 = scratch[(2 * k + 1) * sstride];
-        cd W1 = rfma(T.alpha[1], r1, scale(T.beta[1], r2));
-        cd f = zk - zeta - conj(W1);
-        const double f2 = norm2(f);
-        // Newton on the lens equation z - zeta - conj(W1(z)) = 0 (well conditioned, unlike the
-        // polynomial at small q):  dz = -(f + conj(W2) conj(f)) / (1 - |W2|^2)
-        bool phys = (f2 < 1e-12);                     // the reference's test, multipoles.py:183
-        // physical root: only ever a tiny correction.  Residual in (1e-6, 1e-1): the root noise of
-        // an ill-conditioned polynomial, amplified by |W2| up to 1e7 (faint image next to a low-mass
-        // lens), can push a true image over the threshold; it is kept iff Newton on the lens
-        // equation, started with a minute step (< 1e-7), converges (each step >= 100x smaller than
-        // the one before, down to 1e-10 of the distance to the nearer lens).
-        bool conv = false;
-        double lim = phys ? 1e-10 : 1e-14;
-#pragma unroll 1
-        for (int it = 0; it < 3; ++it) {
-            const cd r1s = csq(r1), r2s = csq(r2);
-            const cd W2 = rfma(T.alpha[2], r1s, scale(T.beta[2], r2s));
-            const double iJ = rcp_step(1.0 - norm2(W2));
-            const cd dz = scale(-iJ, cjfma(W2, conj(f), f));
-            const double dz2 = norm2(dz);
-            // (8 ulp of |z|)^2: steps at the rounding level of z count as converged, not as stalled
-            const double ulp2 = 3.2e-30 * norm2(zk);
-            if (!(dz2 < fmax(lim, ulp2))) break;
-            zk = zk + dz;
-            zs = mk(zk.x + T.s, zk.y);
-            r1 = crcp(zk);
-            r2 = crcp(zs);
-            if (dz2 <= fmax(1e-20 * fmin(norm2(zk), norm2(zs)), ulp2)) { conv = true; break; }
-            lim = 1e-4 * dz2;
-            W1 = rfma(T.alpha[1], r1, scale(T.beta[1], r2));
-            f = zk - zeta - conj(W1);
-        }
-        if (!phys) phys = conv;
-        if (!phys) continue;
-        ++n;
-        // W_k = alpha_k r1^k + beta_k r2^k, multipoles.py:197-201
-        const cd a2 = csq(r1), b2 = csq(r2);
-        const cd a3 = cmul(a2, r1), b3 = cmul(b2, r2);
-        const cd a4 = csq(a2), b4 = csq(b2);
-        const cd W2 = rfma(T.alpha[2], a2, scale(T.beta[2], b2));
-        const cd W3 = rfma(T.alpha[3], a3, scale(T.beta[3], b3));
-        const cd W4 = rfma(T.alpha[4], a4, scale(T.beta[4], b4));
-        cd W5 = mk(0.0, 0.0), W6 = mk(0.0, 0.0);
-        if (ORDER >= 4) {
-            const cd a5 = cmul(a4, r1), b5 = cmul(b4, r2);
-            const cd a6 = csq(a3), b6 = csq(b3);
-            W5 = rfma(T.alpha[5], a5, scale(T.beta[5], b5));
-            W6 = rfma(T.alpha[6], a6, scale(T.beta[6], b6));
-        }
-        const ImageTerms t = image_terms_from_W<ORDER>(W2, W3, W4, W5, W6);
-        const double v2 = fma(sf.h2, t.mu2, t.mu0);
-        A0 += fabs(t.mu0);
-        A2 += fabs(v2);
-        if (ORDER >= 4) A4 += fabs(fma(sf.h4, t.mu4, v2));
-        minJ = fmin(minJ, fabs(1.0 - norm2(W2)));
-    }
-    if (minJ < 1e-3) flags |= MLM_FLAG_NEARCRIT;
-    if (ORDER >= 4 && fabs(A4 - A2) > fabs(A2 - A0)) flags |= MLM_FLAG_SERIES;
-    out.A0 = A0; out.A2 = A2; out.A4 = A4; out.nimg = n; out.flags = flags;
-}
 
 // =======================================================================================
 // Image-tracking path (k_map, k_models, k_points).
