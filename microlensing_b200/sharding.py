@@ -69,11 +69,14 @@ def plan_map(ny: int, rank: int, world: int, nchunks: int = 4, align: int = MAP_
     return ShardPlan(rank, world, lo, n, max_rows, tuple(chunks))
 
 
-def auto_strip(nx: int, rows_per_rank: int, resident_threads: int = 148 * 16 * 32, waves: int = 6) -> int:
-    """Strip length (power of two, 8..64) that leaves every rank about `waves` waves of work items:
-    one work item = one column of one strip; a B200 keeps 148 SMs x 16 warps of them resident."""
+def auto_strip(nx: int, rows_per_rank: int, resident_threads: int = 148 * 16 * 32, waves: int = 12) -> int:
+    """Strip length (power of two, 16..64) that leaves every rank about `waves` waves of work items:
+    one work item = one column of one strip; a B200 keeps 148 SMs x 16 warps of them resident.
+    Measured on the 8192-wide C4 map (tools/time_shards2.py): a launch of w waves of 64-row strips
+    costs about ceil(w + 0.5) block durations, so 1/2, 1/4, 1/8 of the map run best with 32-, 16-,
+    16-row strips (a shorter strip costs ~2000/L more FP64 instructions per pixel in cold solves)."""
     strip = 64
-    while strip > 8 and nx * max(rows_per_rank, 1) // strip < waves * resident_threads:
+    while strip > 16 and nx * max(rows_per_rank, 1) // strip < waves * resident_threads:
         strip //= 2
     return strip
 

@@ -459,8 +459,8 @@ def test_two_gpu_sharded_map_equals_single_gpu(mb, tmp_path, gather, layout):
     ctx = mb._capi.context()
     default = mb.magnification_map(s, q, rho, G, -0.88, -0.8, 1.6 / nx, 1.6 / ny, nx, ny)
     old = ctx.map_strip()
-    assert auto_strip(nx, ny // 2) == 8              # what the workers pinned with align=8
-    ctx.set_map_strip(8)
+    assert auto_strip(nx, ny // 2) == 16 and auto_strip(8192, 8192) == 64 and auto_strip(8192, 1024) == 16
+    ctx.set_map_strip(8)                             # what the workers pinned with align=8
     try:
         one = mb.magnification_map(s, q, rho, G, -0.88, -0.8, 1.6 / nx, 1.6 / ny, nx, ny)
     finally:
