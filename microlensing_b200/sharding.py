@@ -422,7 +422,9 @@ class ShardedModels:
                           for key, item in KEYS if key in self.outputs}
             with torch.cuda.device(self.device):
                 self.comm_stream = torch.cuda.Stream()
-        self.nchunks = 4
+        # pipelining units of the bulk copies: a chunk should still be a few waves of blocks (one block
+        # = one model; ~1000 resident blocks per GPU), small launches pay a start-up/drain phase each
+        self.nchunks = max(1, min(4, (self.hi - self.lo) // 1000))
 
     def compute(self, order=4):
         """Enqueue this rank's models on the current stream (results land in rank 0's buffer)."""
