@@ -631,7 +631,7 @@ int mlm_points(mlm_context* ctx, double s, double q, double rho, double Gamma, c
     make_table(s, q, &T);
     const SourceFactors sf = source_factors(rho, Gamma);
     // consecutive entries per thread: enough threads to fill the GPU (148 SMs x 16 warps) first
-    int seg = ctx->points_segment > 0 ? ctx->points_segment : (int)(n / (148 * 16 * 32));
+    int seg = ctx->points_segment > 0 ? ctx->points_segment : (int)(n / ((int64_t)ctx->sm_count * 16 * 32));
     if (ctx->points_segment <= 0) seg = seg < 1 ? 1 : (seg > 32 ? 32 : seg);
     const int64_t nthreads = (n + seg - 1) / seg;
     const unsigned blocks = (unsigned)((nthreads + MLM_BLOCK - 1) / MLM_BLOCK);

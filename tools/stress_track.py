@@ -10,13 +10,13 @@ from microlensing_b200.batched import lightcurve_coordinates
 ce.lib = ct.libs
 
 
-def run(M=200, T=2000, L=32, seed=1, qlo=1e-4, quadratic=1):
+def run(M=200, T=2000, L=32, seed=1, qlo=1e-4, quadratic=1, slo=0.5, shi=2.0, u0max=0.5):
     ct.libs.emu_set_quadratic(quadratic)      # k_models keeps three levels of root history
     rng = np.random.default_rng(seed)
-    s = np.exp(rng.uniform(np.log(0.5), np.log(2.), M))
+    s = np.exp(rng.uniform(np.log(slo), np.log(shi), M))
     q = np.exp(rng.uniform(np.log(qlo), np.log(1.), M))
     rho = np.exp(rng.uniform(np.log(1e-4), np.log(1e-2), M))
-    u0, al = rng.uniform(-.5, .5, M), rng.uniform(0, 2 * np.pi, M)
+    u0, al = rng.uniform(-u0max, u0max, M), rng.uniform(0, 2 * np.pi, M)
     nbad = 0; worst = 0.0; cold = 0; tot = 0; nflag = 0
     for m in range(M):
         zeta = lightcurve_coordinates(s[m], q[m], u0[m], al[m], -2.0, 4.0 / T, T)
