@@ -400,12 +400,16 @@ __global__ void __launch_bounds__(128, 1) k_fp64_probe(double* out, int iters, c
 // ------------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------------
+#define MLM_HSTAGE_POINTS 4096                          /* results of <= this many positions travel as one block */
+#define MLM_HSTAGE_BYTES (MLM_HSTAGE_POINTS * 26 + 4096)
+
 struct mlm_context {
     int device = 0;
     cudaStream_t stream[2] = {nullptr, nullptr};
     cudaEvent_t ev[2] = {nullptr, nullptr};
     void* dbuf = nullptr;                              // device scratch for *_host entry points
     size_t dbuf_bytes = 0;
+    void* hstage = nullptr;                            // pinned staging for small results (one D2H instead of five)
     double* partial = nullptr;                         // from_wk partial sums
     int partial_blocks = 0;
     std::atomic<int64_t> launches{0};
@@ -497,6 +501,10 @@ int mlm_create(int device, mlm_context** out) {
         }
     }
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (cudaHostAlloc(&ctx->hstage, MLM_HSTAGE_BYTES, cudaHostAllocPortable) != cudaSuccess) {
+        ctx->hstage = nullptr;                         // optional: the general path works without it
+        cudaGetLastError();
+    }
     if (const char* e2 = getenv("MLM_MAP_STRIP")) {
         const int v = atoi(e2);
         if (v >= 1 && v <= 4096) ctx->map_strip = v;
@@ -518,6 +526,7 @@ int mlm_destroy(mlm_context* ctx) {
     DeviceGuard g(ctx->device);
     cudaDeviceSynchronize();
     if (ctx->dbuf) cudaFree(ctx->dbuf);
+    if (ctx->hstage) cudaFreeHost(ctx->hstage);
     if (ctx->partial) cudaFree(ctx->partial);
     for (int i = 0; i < 2; ++i) {
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -886,6 +895,24 @@ int mlm_points_host(mlm_context* ctx, double s, double q, double rho, double Gam
     Scratch sc;
     int rc = carve(ctx, n, true, &sc);
     if (rc) return rc;
+    if (n <= MLM_HSTAGE_POINTS && ctx->hstage) {
+        // small call (example(), a handful of epochs): latency matters, not bandwidth -- one H2D, one kernel,
+        // ONE D2H of the whole result block into pinned staging, then host copies into the caller's arrays
+        cudaStream_t st = ctx->stream[0];
+        const size_t npad = ((size_t)n + 255) & ~(size_t)255;
+        CK(cudaMemcpyAsync(sc.zeta, zeta, n * 16, cudaMemcpyHostToDevice, st));
+        rc = mlm_points(ctx, s, q, rho, Gamma, sc.zeta, n, order, sc.A0, sc.A2, sc.A4, sc.nimg, sc.flags, st);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(ctx->hstage, sc.A0, npad * 26, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const char* h = (const char*)ctx->hstage;
+        if (A0) memcpy(A0, h, n * 8);
+        if (A2) memcpy(A2, h + npad * 8, n * 8);
+        if (A4) memcpy(A4, h + npad * 16, n * 8);
+        if (nimg) memcpy(nimg, h + npad * 24, n);
+        if (flags) memcpy(flags, h + npad * 25, n);
+        return 0;
+    }
     // chunks alternate between the two streams: H2D(k+1) and D2H(k-1) overlap kernel(k)
     int k = 0;
     const int64_t chunk = (n / 8 > MLM_CHUNK_POINTS) ? (n + 7) / 8 : MLM_CHUNK_POINTS;   // at most ~8 chunks
