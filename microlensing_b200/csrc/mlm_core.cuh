@@ -555,10 +555,71 @@ MLM_HD int classify_roots(const LensTable& T, cd zeta, cd* sz, int stride, unsig
             W1 = rfma(T.alpha[1], r1, scale(T.beta[1], r2));
             f = zk - zeta - conj(W1);
         }
-        if (!phys) phys = conv;
+        if (!phys && conv) {
+            // rescued: it must be an image of its own, not a second, noisier root next to an image
+            // that is already counted (q <~ 1e-6: two roots 1e-9 apart next to the planet)
+            phys = true;
+            const double dl2 = fmin(norm2(zk), norm2(zs));
+#pragma unroll
+            for (int j = 0; j < 5; ++j)
+                if (j < k && ((phys_mask >> j) & 1u) && norm2(sz[j * stride] - zk) <= 1e-12 * dl2) phys = false;
+        }
         if (phys) {
             phys_mask |= 1u << k;
             sz[k * stride] = zk;                      // the polished image
+        }
+    }
+    // A binary lens has 3 or 5 images.  An EVEN count means that an image sitting almost on top of a lens
+    // (distance d << 1: a very distant source, or a secondary of q <~ 1e-6) was lost to the rounding noise
+    // of the quintic, which cannot resolve z + s to better than ~1e-16/d relative.  Such an image is found
+    // directly: its position follows from the lens equation with the near lens dominating,
+    //   delta = m_i / conj(p_i - zeta - m_j / conj(p_i - p_j)),   z = p_i + delta,
+    // and Newton on the lens equation from there converges in two or three steps.  It replaces the
+    // non-physical root next to it.  (The reference loses these images too; their magnification is < 1e-12.)
+    {
+        int nphys = 0;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) nphys += (phys_mask >> k) & 1u;
+        if ((nphys & 1) == 0 && nphys < 5) {
+#pragma unroll 1
+            for (int lens = 0; lens < 2; ++lens) {
+                const cd p = mk(lens ? -T.s : 0.0, 0.0);
+                const double mi = lens ? T.beta[1] : T.alpha[1];
+                const double other = lens ? T.alpha[1] / T.s : -T.beta[1] / T.s;   // -m_j / conj(p_i - p_j), real
+                const cd den = mk(p.x - zeta.x + other, zeta.y);                  // conj(p_i - zeta - m_j/conj(p_i - p_j))
+                cd zn = p + scale(mi, crcp(den));
+                const double del2 = norm2(zn - p);
+                if (!(del2 < 1e-4)) continue;            // the image is not close to this lens: nothing was lost here
+                bool conv = false;
+                double lim = 1e300;
+#pragma unroll 1
+                for (int it = 0; it < 8; ++it) {
+                    double dz2, d2, z2;
+                    const cd z1 = lens_newton(T, zeta, zn, dz2, d2, z2);
+                    if (!(dz2 < lim)) break;
+                    zn = z1;
+                    if (dz2 <= fmax(1e-24 * d2, 3.2e-30 * z2)) { conv = true; break; }
+                    lim = 0.25 * dz2;
+                }
+                if (!conv) continue;
+                // already among the images?  else it takes the place of the nearest non-physical root
+                const double dl2 = fmin(norm2(zn), norm2(mk(zn.x + T.s, zn.y)));
+                bool dup = false;
+                int knear = -1;
+                double best = 1e300;
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    const double dist2 = norm2(sz[k * stride] - zn);
+                    if ((phys_mask >> k) & 1u) {
+                        if (dist2 <= 1e-12 * dl2) dup = true;
+                    } else if (!(dist2 >= best)) {       // NaN slots (degenerate polynomial) lose against any number... and win if nothing else
+                        best = dist2; knear = k;
+                    }
+                }
+                if (dup || knear < 0) continue;
+                sz[knear * stride] = zn;
+                phys_mask |= 1u << knear;
+            }
         }
     }
     // stable partition: physical images first
