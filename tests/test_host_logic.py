@@ -277,3 +277,24 @@ def test_logic_warm_started_tracking_equals_cold_solves(emu):
         tot += len(zeta)
     assert worst < 1e-9, worst
     assert cold / tot < 0.12          # tracking is accepted almost everywhere (segment starts are cold)
+
+
+def test_logic_image_count_is_odd_where_the_reference_loses_images(emu):
+    """Very distant sources and secondaries of q <= 1e-5 put an image almost on top of a lens, where the
+    quintic in double precision cannot resolve it: the reference (np.roots + 1e-6 residual test) then counts
+    2 images.  The kernel logic must give the count and the values of the 40-digit evaluation."""
+    from oracle.truth_mp import truth_point
+    from oracle import cassan_oracle as oracle
+    rng = np.random.default_rng(11)
+    cases = [(1.0, 0.5, np.array([1e2 + 0j, 1e3 + 1e3j, -1e4j, 1e6 + 1j])),
+             (1.0, 1e-7, rng.uniform(-0.3, 0.3, 12) + 1j * rng.uniform(-0.3, 0.3, 12)),
+             (1.3, 1e-5, -1.3 + 0.53 + rng.uniform(-0.02, 0.02, 12) + 1j * rng.uniform(-0.02, 0.02, 12))]
+    ref_wrong = 0
+    for s, q, zeta in cases:
+        ni, A, fl = emu.points(s, q, 1e-3, 0.5, zeta)
+        for i, z in enumerate(zeta):
+            t = truth_point(s, q, 1e-3, 0.5, z)
+            assert ni[i] == t[0] and ni[i] in (3, 5), (s, q, z, ni[i], t[0])
+            assert np.allclose(A[i], t[1:4], rtol=1e-12), (s, q, z)
+            ref_wrong += oracle.point_a4(s, q, 1e-3, 0.5, z)[0] != t[0]
+    assert ref_wrong > 10          # the regime is indeed one where the reference miscounts
