@@ -283,6 +283,22 @@ def test_models_chi2_fused_fit(mb):
     assert np.allclose(r2["SA"], (w[None, :] * lc["A2"]).sum(axis=1), rtol=1e-10)
 
 
+def test_image_count_is_odd_where_the_reference_loses_images(mb):
+    """Images almost on top of a lens (very distant source, q <= 1e-5): the reference counts 2, the truth and
+    the kernel 3; values equal the 40-digit evaluation."""
+    from oracle.truth_mp import truth_point
+    rng = np.random.default_rng(11)
+    cases = [(1.0, 0.5, np.array([1e2 + 0j, 1e3 + 1e3j, -1e4j, 1e6 + 1j])),
+             (1.0, 1e-7, rng.uniform(-0.3, 0.3, 12) + 1j * rng.uniform(-0.3, 0.3, 12)),
+             (1.3, 1e-5, -1.3 + 0.53 + rng.uniform(-0.02, 0.02, 12) + 1j * rng.uniform(-0.02, 0.02, 12))]
+    for s, q, zeta in cases:
+        r = mb.magnification_points(s, q, 1e-3, 0.5, zeta)
+        for i, z in enumerate(zeta):
+            t = truth_point(s, q, 1e-3, 0.5, z)
+            assert r["nimg"][i] == t[0], (s, q, z, r["nimg"][i], t[0])
+            assert np.allclose([r["A0"][i], r["A2"][i], r["A4"][i]], t[1:4], rtol=1e-12), (s, q, z)
+
+
 def test_edge_cases(mb, golden_points):
     s, q, rho, G = 1.0, 0.5, 1e-3, 0.5
     z = np.array([0j, -1 + 0j, 1e-9 + 0j, 1e-6 + 1e-6j, -1 + 1e-8j, 50 + 20j])
