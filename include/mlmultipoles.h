@@ -91,7 +91,7 @@ int mlm_set_map_strip(mlm_context* ctx, int strip);
 /* N source positions, one (s,q,rho,Gamma).  zeta: n complex (primary frame), in any order.  Consecutive
  * entries that are close to each other (a light curve along any trajectory, a scan line) are exploited:
  * a thread walks along a run of consecutive entries carrying the images from one to the next and
- * solves cold only at the start of its run, after a jump of more than 0.1 Einstein radii, or where
+ * solves cold only at the start of its run, after a jump of more than 0.02 Einstein radii, or where
  * tracking is rejected; an unordered list costs one cold solve per entry.  The result of an entry
  * agrees with its cold solve to rounding (<= 1e-11 away from caustics), the image count exactly. */
 int mlm_points(mlm_context* ctx, double s, double q, double rho, double Gamma,

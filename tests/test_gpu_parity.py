@@ -194,7 +194,7 @@ def test_points_on_an_uneven_curved_trajectory(mb, s, q):
     n = 30000
     tau = np.cumsum(rng.exponential(1.0, n))
     tau = -1.5 + 3.0 * tau / tau[-1]                                   # uneven epochs
-    tau[n // 3:] += 0.2                                                # a gap (jump > 0.1 -> cold restart)
+    tau[n // 3:] += 0.2                                                # a gap (a jump -> cold restart)
     zeta_cm = (tau + 1j * (0.02 + 0.05 * tau ** 2)) * np.exp(0.3j)      # curved
     zeta = zeta_cm - s * q / (1 + q)
     nb, B0, B2, B4, z, keep, minJ, res = oracle.batch_a4(s, q, rho, G, zeta, return_extra=True)
