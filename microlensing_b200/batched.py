@@ -95,17 +95,33 @@ def magnification_points(s, q, rho, Gamma, zeta, order=4, out=None, device=None,
 
 
 def magnification_map(s, q, rho, Gamma, x0, y0, dx, dy, nx, ny, row0=0, nrows=None, order=4, out=None,
-                      device=None, outputs=ALL_OUTPUTS) -> Magnification:
+                      device=None, outputs=ALL_OUTPUTS, strip=None) -> Magnification:
     """Rows [row0, row0+nrows) of an nx x ny magnification map (centre-of-mass window, pixel-centre
-    sampling); coordinates are generated on the GPU, results land in `out` (nrows, nx)."""
+    sampling); coordinates are generated on the GPU, results land in `out` (nrows, nx).
+
+    `strip` = rows a thread tracks before it starts afresh (a numerical parameter like a tile size, see
+    mlm_set_map_strip).  None: chosen from the size of the WHOLE map (sharding.auto_strip(nx, ny): 64 rows
+    for 8192^2, 16 for 4096^2 and smaller), so that row blocks of one map computed by separate calls --
+    on strip boundaries -- are bit-identical to the map computed at once."""
+    import os
+    from .sharding import auto_strip
     ctx = _capi.context(device)
     nrows = ny - row0 if nrows is None else nrows
     shape = (nrows, nx)
     if out is None:
         out = alloc_outputs(shape, device, pinned=nrows * nx >= (1 << 16), outputs=outputs)
     _check_out(out, shape)
-    ctx.check(ctx.lib.mlm_map_host(ctx.handle, s, q, rho, Gamma, x0, y0, dx, dy, nx, row0, nrows, order,
-                                   *_out_ptrs(out)), "mlm_map_host")
+    old = ctx.map_strip()
+    if strip is None:
+        strip = old if os.environ.get("MLM_MAP_STRIP") else auto_strip(nx, ny)      # the env var pins it (experiments)
+    if strip != old:
+        ctx.set_map_strip(strip)
+    try:
+        ctx.check(ctx.lib.mlm_map_host(ctx.handle, s, q, rho, Gamma, x0, y0, dx, dy, nx, row0, nrows, order,
+                                       *_out_ptrs(out)), "mlm_map_host")
+    finally:
+        if strip != old:
+            ctx.set_map_strip(old)
     return out
 
 

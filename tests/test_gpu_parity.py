@@ -333,9 +333,10 @@ def test_row_sharding_is_bitwise_identical(mb):
     s, q, rho, G = 1.0, 0.5, 1e-3, 0.5
     nx, ny = 256, 203
     x0, y0, dx, dy = -0.88, -0.8, 1.6 / nx, 1.6 / ny
+    from microlensing_b200.sharding import auto_strip
     full = mb.magnification_map(s, q, rho, G, x0, y0, dx, dy, nx, ny)
-    strip = mb._capi.context().lib.mlm_map_strip(mb._capi.context().handle)
-    assert strip == 64
+    strip = auto_strip(nx, ny)                      # what the host API picks for this map, whatever the row block
+    assert strip == 16 and mb._capi.context().map_strip() == 64          # the context default is untouched
     for world in (2, 3, 8):
         parts = []
         for r in range(world):
@@ -349,8 +350,12 @@ def test_row_sharding_is_bitwise_identical(mb):
     for world in (2, 3):
         bufs = [torch.full((ny * nx,), -1.0, dtype=torch.float64, device="cuda") for _ in range(3)] + \
                [torch.full((ny * nx,), 255, dtype=torch.uint8, device="cuda") for _ in range(2)]
-        for r in range(world):
-            map_strips_device(s, q, rho, G, x0, y0, dx, dy, nx, 0, ny, r, world, *bufs)
+        mb._capi.context().set_map_strip(strip)          # the device API takes the context's strip length
+        try:
+            for r in range(world):
+                map_strips_device(s, q, rho, G, x0, y0, dx, dy, nx, 0, ny, r, world, *bufs)
+        finally:
+            mb._capi.context().set_map_strip(0)
         torch.cuda.synchronize()
         for k, b in zip(("A0", "A2", "A4", "nimg", "flags"), bufs):
             assert np.array_equal(b.cpu().numpy().reshape(ny, nx), full[k]), (world, k)
@@ -367,7 +372,8 @@ def test_device_pointer_api_and_sharded_map(mb):
     s, q, rho, G = 0.8, 0.1, 1e-3, 0.5
     nx = ny = 192
     x0, y0, dx, dy = 0.11 - 0.75, -0.75, 1.5 / nx, 1.5 / ny
-    strip = mb._capi.context().map_strip()
+    from microlensing_b200.sharding import auto_strip
+    strip = auto_strip(nx, ny)                       # = what magnification_map picks for this map
     sm = ShardedMap(nx, ny, 0, 1, nchunks=3, align=strip)
     sm.compute(s, q, rho, G, x0, y0, dx, dy)
     torch.cuda.synchronize()
@@ -400,7 +406,12 @@ def test_host_chunking_is_bitwise_neutral(mb):
     n = nrows * nx
     bufs = [torch.empty(n, dtype=torch.float64, device="cuda") for _ in range(3)] + \
            [torch.empty(n, dtype=torch.uint8, device="cuda") for _ in range(2)]
-    map_device(s, q, rho, G, x0, y0, dx, dy, nx, row0, nrows, *bufs)
+    from microlensing_b200.sharding import auto_strip
+    mb._capi.context().set_map_strip(auto_strip(nx, ny))
+    try:
+        map_device(s, q, rho, G, x0, y0, dx, dy, nx, row0, nrows, *bufs)
+    finally:
+        mb._capi.context().set_map_strip(0)
     torch.cuda.synchronize()
     for k, b in zip(("A0", "A2", "A4", "nimg", "flags"), bufs):
         assert np.array_equal(b.cpu().numpy().reshape(nrows, nx), host[k]), k
@@ -472,15 +483,9 @@ def test_two_gpu_sharded_map_equals_single_gpu(mb, tmp_path, gather, layout):
     # the single-GPU map with the strip length the sharded run picked (auto_strip) is bit-identical;
     # with the default strip it agrees to rounding
     from microlensing_b200.sharding import auto_strip
-    ctx = mb._capi.context()
     default = mb.magnification_map(s, q, rho, G, -0.88, -0.8, 1.6 / nx, 1.6 / ny, nx, ny)
-    old = ctx.map_strip()
     assert auto_strip(nx, ny // 2) == 16 and auto_strip(8192, 8192) == 64 and auto_strip(8192, 1024) == 16
-    ctx.set_map_strip(8)                             # what the workers pinned with align=8
-    try:
-        one = mb.magnification_map(s, q, rho, G, -0.88, -0.8, 1.6 / nx, 1.6 / ny, nx, ny)
-    finally:
-        ctx.set_map_strip(old)
+    one = mb.magnification_map(s, q, rho, G, -0.88, -0.8, 1.6 / nx, 1.6 / ny, nx, ny, strip=8)   # the workers' align=8
     for k in ("A0", "A2", "A4", "nimg", "flags"):
         assert np.array_equal(got[k], one[k]), k
     assert np.array_equal(got["nimg"], default["nimg"])
