@@ -1,2 +1,6 @@
-version_info = (0, 4, 0)          # tracks the reference's microlensing/_version.py:1
-__version__ = '.'.join(map(str, version_info))
+"""Release number of the B200-native package.
+
+Kept equal to the release of ArnaudCassan/microlensing whose ``multipoles`` path it replaces, so that
+``microlensing.__version__`` reads the same for code that checks it."""
+__version__ = "0.4.0"
+version_info = tuple(int(part) for part in __version__.split("."))
