@@ -136,6 +136,20 @@ int mlm_models_host(mlm_context* ctx, const double* s, const double* q, const do
                     const double* u0, const double* alpha, int64_t M, double tau0, double dtau, int64_t T, int order,
                     double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags);
 
+/* The same with OBSERVATION TIMES instead of a uniform grid ("in-kernel trajectory
+ * zeta(t; t0, tE, u0, alpha)"): epoch t of model m is at tau = (times[t] - t0[m]) / tE[m]; t0, tE are device
+ * arrays of length M (NULL: 0 and 1, i.e. times are already in Einstein times from closest approach).
+ * Unevenly spaced epochs are tracked with the extrapolation scaled by the ratio of successive steps; a gap of
+ * more than 0.02 Einstein times restarts cold. */
+int mlm_models_times(mlm_context* ctx, const double* s, const double* q, const double* rho, const double* Gamma,
+                     const double* u0, const double* alpha, const double* t0, const double* tE, int64_t M,
+                     const double* times, int64_t T, int order,
+                     double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags, void* stream);
+int mlm_models_times_host(mlm_context* ctx, const double* s, const double* q, const double* rho, const double* Gamma,
+                          const double* u0, const double* alpha, const double* t0, const double* tE, int64_t M,
+                          const double* times, int64_t T, int order,
+                          double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags);
+
 /* Model grid with the light-curve fit fused in ("fused chi^2 reduction against observed
  * fluxes"): same models and epochs as mlm_models, but instead of M x T magnifications the kernel returns,
  * per model, the least-squares linear flux fit F_t = Fs A_t + Fb of the model magnifications A_t (A4 for
@@ -148,6 +162,16 @@ int mlm_models_chi2(mlm_context* ctx, const double* s, const double* q, const do
 int mlm_models_chi2_host(mlm_context* ctx, const double* s, const double* q, const double* rho, const double* Gamma,
                          const double* u0, const double* alpha, int64_t M, double tau0, double dtau, int64_t T, int order,
                          const double* flux, const double* weight, double* stats);
+
+/* ... and against a light curve observed at times[T] (t0, tE per model as in mlm_models_times). */
+int mlm_models_chi2_times(mlm_context* ctx, const double* s, const double* q, const double* rho, const double* Gamma,
+                          const double* u0, const double* alpha, const double* t0, const double* tE, int64_t M,
+                          const double* times, int64_t T, int order,
+                          const double* flux, const double* weight, double* stats, void* stream);
+int mlm_models_chi2_times_host(mlm_context* ctx, const double* s, const double* q, const double* rho, const double* Gamma,
+                               const double* u0, const double* alpha, const double* t0, const double* tE, int64_t M,
+                               const double* times, int64_t T, int order,
+                               const double* flux, const double* weight, double* stats);
 
 /* ---- drop-ins for the individual reference functions ------------------------------------ */
 

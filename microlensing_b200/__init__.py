@@ -5,4 +5,4 @@ from ._version import version_info, __version__  # noqa: F401
 from . import multipoles  # noqa: F401
 from .multipoles import Rkp  # noqa: F401
 from .batched import (magnification_points, magnification_map, magnification_models, models_chi2,  # noqa: F401
-                      map_coordinates, lightcurve_coordinates, alloc_outputs)
+                      map_coordinates, lightcurve_coordinates, lightcurve_coordinates_at, alloc_outputs)

@@ -42,6 +42,10 @@ SIGNATURES = {
     "mlm_map_host": [_P, _D, _D, _D, _D, _D, _D, _D, _D, _L, _L, _L, _I, _P, _P, _P, _P, _P],
     "mlm_models": [_P, _P, _P, _P, _P, _P, _P, _L, _D, _D, _L, _I, _P, _P, _P, _P, _P, _P],
     "mlm_models_host": [_P, _P, _P, _P, _P, _P, _P, _L, _D, _D, _L, _I, _P, _P, _P, _P, _P],
+    "mlm_models_times": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P, _L, _I, _P, _P, _P, _P, _P, _P],
+    "mlm_models_times_host": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P, _L, _I, _P, _P, _P, _P, _P],
+    "mlm_models_chi2_times": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P, _L, _I, _P, _P, _P, _P],
+    "mlm_models_chi2_times_host": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P, _L, _I, _P, _P, _P],
     "mlm_models_chi2": [_P, _P, _P, _P, _P, _P, _P, _L, _D, _D, _L, _I, _P, _P, _P, _P],
     "mlm_models_chi2_host": [_P, _P, _P, _P, _P, _P, _P, _L, _D, _D, _L, _I, _P, _P, _P],
     "mlm_from_wk": [_P, _P, _L, _I, _D, _D, _P, _P],

@@ -14,7 +14,7 @@ from . import _capi
 
 __all__ = ["Magnification", "magnification_points", "magnification_map", "magnification_models", "models_chi2",
            "models_chi2_device",
-           "map_coordinates", "lightcurve_coordinates", "alloc_outputs", "ALL_OUTPUTS", "map_device", "map_strips_device", "points_device",
+           "map_coordinates", "lightcurve_coordinates", "lightcurve_coordinates_at", "alloc_outputs", "ALL_OUTPUTS", "map_device", "map_strips_device", "points_device",
            "models_device"]
 
 
@@ -64,6 +64,16 @@ def map_coordinates(s, q, x0, y0, dx, dy, nx, ny, row0=0, nrows=None):
     x = (x0 + (c + 0.5) * dx) + (-(s * q / (1. + q)))
     y = y0 + (r + 0.5) * dy
     return x[None, :] + 1j * y[:, None]
+
+
+def lightcurve_coordinates_at(s, q, u0, alpha, times, t0=0.0, tE=1.0):
+    """Primary-frame zeta at observation times: tau = (times - t0) / tE, zeta_cm = (tau + i u0) exp(i alpha),
+    same arithmetic as the models kernel (mlm_models_times)."""
+    tau = (np.asarray(times, dtype=np.float64) + (-t0)) / tE
+    ca, sa = np.cos(alpha), np.sin(alpha)
+    zx = (tau * ca + (-(u0 * sa))) + (-(s * q / (1. + q)))
+    zy = tau * sa + u0 * ca
+    return zx + 1j * zy
 
 
 def lightcurve_coordinates(s, q, u0, alpha, tau0, dtau, T):
@@ -125,43 +135,80 @@ def magnification_map(s, q, rho, Gamma, x0, y0, dx, dy, nx, ny, row0=0, nrows=No
     return out
 
 
-def magnification_models(s, q, rho, Gamma, u0, alpha, tau0, dtau, T, order=4, out=None, device=None,
-                         outputs=ALL_OUTPUTS) -> Magnification:
-    """Batched fit grid: M models (arrays s, q, rho, Gamma, u0, alpha of length M) x T epochs."""
-    ctx = _capi.context(device)
-    arrs = [np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float64), np.shape(s)))
-            for a in (s, q, rho, Gamma, u0, alpha)]
-    M = arrs[0].size
+def _model_arrays(what, s, q, rho, Gamma, u0, alpha, t0=None, tE=None):
+    names = (s, q, rho, Gamma, u0, alpha) if t0 is None and tE is None else \
+        (s, q, rho, Gamma, u0, alpha, 0.0 if t0 is None else t0, 1.0 if tE is None else tE)
+    arrs = [np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float64), np.shape(s))) for a in names]
     if not (np.all(arrs[0] > 0) and np.all(arrs[1] > 0)):
-        raise ValueError("magnification_models: s and q must be positive")
+        raise ValueError(f"{what}: s and q must be positive")
+    if len(arrs) == 8 and not np.all(arrs[7] > 0):
+        raise ValueError(f"{what}: tE must be positive")
+    return arrs
+
+
+def magnification_models(s, q, rho, Gamma, u0, alpha, tau0=None, dtau=None, T=None, order=4, out=None, device=None,
+                         outputs=ALL_OUTPUTS, times=None, t0=None, tE=None) -> Magnification:
+    """Batched fit grid: M models (arrays s, q, rho, Gamma, u0, alpha of length M) x T epochs, either on the
+    uniform grid tau = tau0 + t dtau, or at observation `times` (any spacing) with per-model (or scalar) time of
+    closest approach t0 and Einstein time tE: tau = (times - t0) / tE."""
+    ctx = _capi.context(device)
+    if times is None:
+        if tau0 is None or dtau is None or T is None:
+            raise ValueError("magnification_models: give (tau0, dtau, T) or times=")
+        arrs = _model_arrays("magnification_models", s, q, rho, Gamma, u0, alpha)
+    else:
+        times = np.ascontiguousarray(times, dtype=np.float64).ravel()
+        T = times.size
+        arrs = _model_arrays("magnification_models", s, q, rho, Gamma, u0, alpha, 0.0 if t0 is None else t0,
+                             1.0 if tE is None else tE)
+    M = arrs[0].size
     shape = (M, T)
     if out is None:
         out = alloc_outputs(shape, device, pinned=M * T >= (1 << 16), outputs=outputs)
     _check_out(out, shape)
-    ctx.check(ctx.lib.mlm_models_host(ctx.handle, *[_capi.ptr(a) for a in arrs], M, tau0, dtau, T, order,
-                                      *_out_ptrs(out)), "mlm_models_host")
+    if times is None:
+        ctx.check(ctx.lib.mlm_models_host(ctx.handle, *[_capi.ptr(a) for a in arrs], M, tau0, dtau, T, order,
+                                          *_out_ptrs(out)), "mlm_models_host")
+    else:
+        ctx.check(ctx.lib.mlm_models_times_host(ctx.handle, *[_capi.ptr(a) for a in arrs], M, _capi.ptr(times), T, order,
+                                                *_out_ptrs(out)), "mlm_models_times_host")
     return out
 
 
-def models_chi2(s, q, rho, Gamma, u0, alpha, tau0, dtau, flux, sigma, order=4, device=None) -> dict:
+def models_chi2(s, q, rho, Gamma, u0, alpha, tau0=None, dtau=None, flux=None, sigma=None, order=4, device=None,
+                times=None, t0=None, tE=None) -> dict:
     """Fit statistics of a grid of M models against ONE observed light curve: the model
     magnifications never leave the GPU.  `flux`, `sigma`: observed fluxes and their errors at the epochs
-    tau_t = tau0 + t dtau.  Returns arrays of length M: chi2 (minimised over the source and blend fluxes Fs, Fb
+    tau_t = tau0 + t dtau, or at the observation `times` with per-model (or scalar) t0, tE:
+    tau = (times - t0) / tE.  Returns arrays of length M: chi2 (minimised over the source and blend fluxes Fs, Fb
     of F = Fs A + Fb), Fs, Fb, the sums SA, SAA, SAF, and the counts n5 (5-image epochs), nflag."""
     ctx = _capi.context(device)
-    arrs = [np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float64), np.shape(s)))
-            for a in (s, q, rho, Gamma, u0, alpha)]
+    if flux is None or sigma is None:
+        raise ValueError("models_chi2: flux and sigma are required")
+    if times is None:
+        if tau0 is None or dtau is None:
+            raise ValueError("models_chi2: give (tau0, dtau) or times=")
+        arrs = _model_arrays("models_chi2", s, q, rho, Gamma, u0, alpha)
+    else:
+        times = np.ascontiguousarray(times, dtype=np.float64).ravel()
+        arrs = _model_arrays("models_chi2", s, q, rho, Gamma, u0, alpha, 0.0 if t0 is None else t0,
+                             1.0 if tE is None else tE)
     M = arrs[0].size
-    if not (np.all(arrs[0] > 0) and np.all(arrs[1] > 0)):
-        raise ValueError("models_chi2: s and q must be positive")
     flux = np.ascontiguousarray(flux, dtype=np.float64).ravel()
+    if times is not None and times.size != flux.size:
+        raise ValueError("models_chi2: times and flux must have the same length")
     sigma = np.ascontiguousarray(np.broadcast_to(np.asarray(sigma, dtype=np.float64), flux.shape))
     if not np.all(sigma > 0):
         raise ValueError("models_chi2: sigma must be positive")
     w = 1.0 / (sigma * sigma)
     stats = np.empty((M, 8), dtype=np.float64)
-    ctx.check(ctx.lib.mlm_models_chi2_host(ctx.handle, *[_capi.ptr(a) for a in arrs], M, tau0, dtau, flux.size, order,
-                                           _capi.ptr(flux), _capi.ptr(w), _capi.ptr(stats)), "mlm_models_chi2_host")
+    if times is None:
+        ctx.check(ctx.lib.mlm_models_chi2_host(ctx.handle, *[_capi.ptr(a) for a in arrs], M, tau0, dtau, flux.size, order,
+                                               _capi.ptr(flux), _capi.ptr(w), _capi.ptr(stats)), "mlm_models_chi2_host")
+    else:
+        ctx.check(ctx.lib.mlm_models_chi2_times_host(ctx.handle, *[_capi.ptr(a) for a in arrs], M, _capi.ptr(times),
+                                                     flux.size, order, _capi.ptr(flux), _capi.ptr(w), _capi.ptr(stats)),
+                  "mlm_models_chi2_times_host")
     keys = ("chi2", "Fs", "Fb", "SA", "SAA", "SAF", "n5", "nflag")
     return Magnification({k: stats[:, i].copy() for i, k in enumerate(keys)})
 

@@ -152,11 +152,44 @@ k_map(const __grid_constant__ LensTable T, const SourceFactors sf, double x0, do
 // seg depends only on the number of epochs, so sharding the models over ranks does not change
 // a single bit of any model's light curve.
 #define MLM_MODELS_BLOCK 64
+
+// Epochs of the light curves of a model grid: tau_t = tau0 + t dtau (uniform grid, times == NULL) or
+// tau_t = (times[t] - t0[m]) / tE[m] (observation times; t0, tE per model, NULL = 0 and 1).
+struct Epochs {
+    double tau0, dtau;
+    const double* times;
+    const double* t0;
+    const double* tE;
+};
+
+__device__ __forceinline__ double epoch_tau(const Epochs& ep, int64_t t, double t0m, double tEm) {
+    if (ep.times) return __ddiv_rn(__dadd_rn(__ldg(ep.times + t), -t0m), tEm);
+    return __dadd_rn(ep.tau0, __dmul_rn((double)t, ep.dtau));
+}
+
+// One epoch of a light-curve walk: unevenly spaced epochs scale the extrapolation by the ratio of successive
+// steps in tau (the source moves at unit speed in tau), a step of more than 0.02 restarts cold.
+__device__ __forceinline__ double epoch_ratio(const Epochs& ep, double tau, double& tau_prev, double& dt_prev,
+                                              TrackState& st) {
+    double ratio = 1.0;
+    if (ep.times) {
+        const double dt = tau - tau_prev;
+        if (st.hist >= 1 && !(fabs(dt) <= 0.02)) st.hist = 0;
+        if (st.hist >= 2) {
+            ratio = dt / dt_prev;
+            if (!(ratio > 0.0 && ratio < 4.0)) st.hist = 1;
+        }
+        tau_prev = tau;
+        dt_prev = dt;
+    }
+    return ratio;
+}
+
 template <int ORDER>
 __global__ void __launch_bounds__(MLM_MODELS_BLOCK, 6)
 k_models(const double* __restrict__ s, const double* __restrict__ q, const double* __restrict__ rho,
          const double* __restrict__ Gamma, const double* __restrict__ u0, const double* __restrict__ alpha,
-         int64_t M, double tau0, double dtau, int64_t Tn, int seg, double* __restrict__ A0,
+         int64_t M, const Epochs ep, int64_t Tn, int seg, double* __restrict__ A0,
          double* __restrict__ A2, double* __restrict__ A4, uint8_t* __restrict__ nimg, uint8_t* __restrict__ flags) {
     __shared__ LensTable T;
     __shared__ SourceFactors sf;
@@ -179,17 +212,20 @@ k_models(const double* __restrict__ s, const double* __restrict__ q, const doubl
         __syncthreads();
         const double u = u0[m];
         const double ur1 = __dmul_rn(u, rot[1]), ur0 = __dmul_rn(u, rot[0]);
+        const double t0m = ep.t0 ? ep.t0[m] : 0.0, tEm = ep.tE ? ep.tE[m] : 1.0;
         for (int64_t sg = (int64_t)blockIdx.x * MLM_MODELS_BLOCK + threadIdx.x; sg < nseg;
              sg += (int64_t)gridDim.x * MLM_MODELS_BLOCK) {
             const int64_t t0 = sg * seg;
             const int64_t t1 = (t0 + seg < Tn) ? t0 + seg : Tn;
             TrackState st;
             st.hist = 0; st.nimg = 0;
+            double tau_prev = 0.0, dt_prev = 1.0;
             for (int64_t t = t0; t < t1; ++t) {
                 // compiler barrier: the table is re-read from shared memory where it is used instead of
                 // being hoisted out of the loop into ~40 live registers
                 asm volatile("" ::: "memory");
-                const double tau = __dadd_rn(tau0, __dmul_rn((double)t, dtau));
+                const double tau = epoch_tau(ep, t, t0m, tEm);
+                const double ratio = epoch_ratio(ep, tau, tau_prev, dt_prev, st);
                 // zeta_cm = (tau + i u0) (cos a + i sin a), then shift to the primary frame
                 const double zx = __dadd_rn(__dadd_rn(__dmul_rn(tau, rot[0]), -ur1), -rot[2]);
                 const double zy = __dadd_rn(__dmul_rn(tau, rot[1]), ur0);
@@ -198,7 +234,7 @@ k_models(const double* __restrict__ s, const double* __restrict__ q, const doubl
                 PointResult res;
                 res.flags = 0;
                 lens_polynomial(T, zeta, c);
-                advance_images(T, zeta, c, sz, szp, szpp, MLM_MODELS_BLOCK, st, res.flags);
+                advance_images(T, zeta, c, sz, szp, szpp, MLM_MODELS_BLOCK, st, res.flags, ratio);
                 sum_images<ORDER>(T, sf, sz, MLM_MODELS_BLOCK, st.nimg, res);
                 store_result(res, m * Tn + t, A0, A2, A4, nimg, flags);
             }
@@ -216,7 +252,7 @@ template <int ORDER>
 __global__ void __launch_bounds__(MLM_MODELS_BLOCK, 6)
 k_models_chi2(const double* __restrict__ s, const double* __restrict__ q, const double* __restrict__ rho,
               const double* __restrict__ Gamma, const double* __restrict__ u0, const double* __restrict__ alpha,
-              int64_t M, double tau0, double dtau, int64_t Tn, int seg, const double* __restrict__ flux,
+              int64_t M, const Epochs ep, int64_t Tn, int seg, const double* __restrict__ flux,
               const double* __restrict__ weight, double* __restrict__ stats) {
     __shared__ LensTable T;
     __shared__ SourceFactors sf;
@@ -240,15 +276,18 @@ k_models_chi2(const double* __restrict__ s, const double* __restrict__ q, const 
         __syncthreads();
         const double u = u0[m];
         const double ur1 = __dmul_rn(u, rot[1]), ur0 = __dmul_rn(u, rot[0]);
+        const double t0m = ep.t0 ? ep.t0[m] : 0.0, tEm = ep.tE ? ep.tE[m] : 1.0;
         double a_w = 0.0, a_wa = 0.0, a_waa = 0.0, a_wf = 0.0, a_waf = 0.0, a_wff = 0.0, a_n5 = 0.0, a_nf = 0.0;
         for (int64_t sg = threadIdx.x; sg < nseg; sg += MLM_MODELS_BLOCK) {
             const int64_t t0 = sg * seg;
             const int64_t t1 = (t0 + seg < Tn) ? t0 + seg : Tn;
             TrackState st;
             st.hist = 0; st.nimg = 0;
+            double tau_prev = 0.0, dt_prev = 1.0;
             for (int64_t t = t0; t < t1; ++t) {
                 asm volatile("" ::: "memory");
-                const double tau = __dadd_rn(tau0, __dmul_rn((double)t, dtau));
+                const double tau = epoch_tau(ep, t, t0m, tEm);
+                const double ratio = epoch_ratio(ep, tau, tau_prev, dt_prev, st);
                 const double zx = __dadd_rn(__dadd_rn(__dmul_rn(tau, rot[0]), -ur1), -rot[2]);
                 const double zy = __dadd_rn(__dmul_rn(tau, rot[1]), ur0);
                 const cd zeta = mk(zx, zy);
@@ -256,7 +295,7 @@ k_models_chi2(const double* __restrict__ s, const double* __restrict__ q, const 
                 PointResult res;
                 res.flags = 0;
                 lens_polynomial(T, zeta, c);
-                advance_images(T, zeta, c, sz, szp, szpp, MLM_MODELS_BLOCK, st, res.flags);
+                advance_images(T, zeta, c, sz, szp, szpp, MLM_MODELS_BLOCK, st, res.flags, ratio);
                 sum_images<ORDER>(T, sf, sz, MLM_MODELS_BLOCK, st.nimg, res);
                 const double A = (ORDER >= 4) ? res.A4 : res.A2;
                 const double w = __ldg(weight + t), f = __ldg(flux + t);
@@ -710,14 +749,14 @@ int mlm_map(mlm_context* ctx, double s, double q, double rho, double Gamma, doub
 
 static int models_segment(mlm_context* ctx, int64_t Tn);
 
-int mlm_models(mlm_context* ctx, const double* s, const double* q, const double* rho, const double* Gamma,
-               const double* u0, const double* alpha, int64_t M, double tau0, double dtau, int64_t Tn, int order,
-               double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags, void* stream) {
-    if (!ctx) return fail(ctx, MLM_EINVAL, "mlm_models: NULL context");
-    if (M < 0 || Tn < 0 || (order != 2 && order != 4)) return fail(ctx, MLM_EINVAL, "mlm_models: bad argument");
+static int launch_models(mlm_context* ctx, const char* who, const double* s, const double* q, const double* rho,
+                         const double* Gamma, const double* u0, const double* alpha, int64_t M, const Epochs& ep,
+                         int64_t Tn, int order, double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags,
+                         void* stream) {
+    if (!ctx) return fail(ctx, MLM_EINVAL, who);
+    if (M < 0 || Tn < 0 || (order != 2 && order != 4)) return fail(ctx, MLM_EINVAL, who);
     if (M == 0 || Tn == 0) return 0;
-    if (!s || !q || !rho || !Gamma || !u0 || !alpha || !(A0 || A2 || A4 || nimg || flags))
-        return fail(ctx, MLM_EINVAL, "mlm_models: NULL buffer");
+    if (!s || !q || !rho || !Gamma || !u0 || !alpha || !(A0 || A2 || A4 || nimg || flags)) return fail(ctx, MLM_EINVAL, who);
     DeviceGuard g(ctx->device);
     const int seg = models_segment(ctx, Tn);
     const int64_t nseg = (Tn + seg - 1) / seg;
@@ -726,12 +765,30 @@ int mlm_models(mlm_context* ctx, const double* s, const double* q, const double*
     dim3 grid((unsigned)bx, (unsigned)(M < 65535 ? M : 65535));
     cudaStream_t st = pick(ctx, stream);
     if (order == 4)
-        k_models<4><<<grid, MLM_MODELS_BLOCK, 0, st>>>(s, q, rho, Gamma, u0, alpha, M, tau0, dtau, Tn, seg, A0, A2, A4, nimg, flags);
+        k_models<4><<<grid, MLM_MODELS_BLOCK, 0, st>>>(s, q, rho, Gamma, u0, alpha, M, ep, Tn, seg, A0, A2, A4, nimg, flags);
     else
-        k_models<2><<<grid, MLM_MODELS_BLOCK, 0, st>>>(s, q, rho, Gamma, u0, alpha, M, tau0, dtau, Tn, seg, A0, A2, A4, nimg, flags);
+        k_models<2><<<grid, MLM_MODELS_BLOCK, 0, st>>>(s, q, rho, Gamma, u0, alpha, M, ep, Tn, seg, A0, A2, A4, nimg, flags);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;
+}
+
+int mlm_models(mlm_context* ctx, const double* s, const double* q, const double* rho, const double* Gamma,
+               const double* u0, const double* alpha, int64_t M, double tau0, double dtau, int64_t Tn, int order,
+               double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags, void* stream) {
+    const Epochs ep = {tau0, dtau, nullptr, nullptr, nullptr};
+    return launch_models(ctx, "mlm_models: bad argument", s, q, rho, Gamma, u0, alpha, M, ep, Tn, order, A0, A2, A4, nimg,
+                         flags, stream);
+}
+
+int mlm_models_times(mlm_context* ctx, const double* s, const double* q, const double* rho, const double* Gamma,
+                     const double* u0, const double* alpha, const double* t0, const double* tE, int64_t M,
+                     const double* times, int64_t Tn, int order, double* A0, double* A2, double* A4, uint8_t* nimg,
+                     uint8_t* flags, void* stream) {
+    if (Tn > 0 && !times) return fail(ctx, MLM_EINVAL, "mlm_models_times: NULL times");
+    const Epochs ep = {0.0, 0.0, times, t0, tE};
+    return launch_models(ctx, "mlm_models_times: bad argument", s, q, rho, Gamma, u0, alpha, M, ep, Tn, order, A0, A2, A4,
+                         nimg, flags, stream);
 }
 
 static int models_segment(mlm_context* ctx, int64_t Tn) {
@@ -741,56 +798,97 @@ static int models_segment(mlm_context* ctx, int64_t Tn) {
     return seg;
 }
 
-int mlm_models_chi2(mlm_context* ctx, const double* s, const double* q, const double* rho, const double* Gamma,
-                    const double* u0, const double* alpha, int64_t M, double tau0, double dtau, int64_t Tn, int order,
-                    const double* flux, const double* weight, double* stats, void* stream) {
-    if (!ctx) return fail(ctx, MLM_EINVAL, "mlm_models_chi2: NULL context");
-    if (M < 0 || Tn < 0 || (order != 2 && order != 4)) return fail(ctx, MLM_EINVAL, "mlm_models_chi2: bad argument");
+static int launch_models_chi2(mlm_context* ctx, const char* who, const double* s, const double* q, const double* rho,
+                              const double* Gamma, const double* u0, const double* alpha, int64_t M, const Epochs& ep,
+                              int64_t Tn, int order, const double* flux, const double* weight, double* stats,
+                              void* stream) {
+    if (!ctx) return fail(ctx, MLM_EINVAL, who);
+    if (M < 0 || Tn < 0 || (order != 2 && order != 4)) return fail(ctx, MLM_EINVAL, who);
     if (M == 0) return 0;
-    if (!s || !q || !rho || !Gamma || !u0 || !alpha || !stats || (Tn > 0 && (!flux || !weight)))
-        return fail(ctx, MLM_EINVAL, "mlm_models_chi2: NULL buffer");
+    if (!s || !q || !rho || !Gamma || !u0 || !alpha || !stats || (Tn > 0 && (!flux || !weight))) return fail(ctx, MLM_EINVAL, who);
     DeviceGuard g(ctx->device);
     const int seg = models_segment(ctx, Tn);
     const unsigned blocks = (unsigned)(M < 1048576 ? M : 1048576);
     cudaStream_t st = pick(ctx, stream);
     if (order == 4)
-        k_models_chi2<4><<<blocks, MLM_MODELS_BLOCK, 0, st>>>(s, q, rho, Gamma, u0, alpha, M, tau0, dtau, Tn, seg, flux, weight, stats);
+        k_models_chi2<4><<<blocks, MLM_MODELS_BLOCK, 0, st>>>(s, q, rho, Gamma, u0, alpha, M, ep, Tn, seg, flux, weight, stats);
     else
-        k_models_chi2<2><<<blocks, MLM_MODELS_BLOCK, 0, st>>>(s, q, rho, Gamma, u0, alpha, M, tau0, dtau, Tn, seg, flux, weight, stats);
+        k_models_chi2<2><<<blocks, MLM_MODELS_BLOCK, 0, st>>>(s, q, rho, Gamma, u0, alpha, M, ep, Tn, seg, flux, weight, stats);
     ctx->launches++;
     CK(cudaGetLastError());
+    return 0;
+}
+
+int mlm_models_chi2(mlm_context* ctx, const double* s, const double* q, const double* rho, const double* Gamma,
+                    const double* u0, const double* alpha, int64_t M, double tau0, double dtau, int64_t Tn, int order,
+                    const double* flux, const double* weight, double* stats, void* stream) {
+    const Epochs ep = {tau0, dtau, nullptr, nullptr, nullptr};
+    return launch_models_chi2(ctx, "mlm_models_chi2: bad argument", s, q, rho, Gamma, u0, alpha, M, ep, Tn, order, flux,
+                              weight, stats, stream);
+}
+
+int mlm_models_chi2_times(mlm_context* ctx, const double* s, const double* q, const double* rho, const double* Gamma,
+                          const double* u0, const double* alpha, const double* t0, const double* tE, int64_t M,
+                          const double* times, int64_t Tn, int order, const double* flux, const double* weight,
+                          double* stats, void* stream) {
+    if (Tn > 0 && !times) return fail(ctx, MLM_EINVAL, "mlm_models_chi2_times: NULL times");
+    const Epochs ep = {0.0, 0.0, times, t0, tE};
+    return launch_models_chi2(ctx, "mlm_models_chi2_times: bad argument", s, q, rho, Gamma, u0, alpha, M, ep, Tn, order,
+                              flux, weight, stats, stream);
+}
+
+// host variant of both: npar = 6 (uniform epochs) or 8 (+ t0, tE) parameter arrays, times optional
+static int models_chi2_host_impl(mlm_context* ctx, const char* who, const double* const* hp, int npar, int64_t M,
+                                 double tau0, double dtau, const double* times, int64_t Tn, int order,
+                                 const double* flux, const double* weight, double* stats) {
+    if (!ctx) return fail(ctx, MLM_EINVAL, who);
+    if (M < 0 || Tn < 0 || (order != 2 && order != 4)) return fail(ctx, MLM_EINVAL, who);
+    if (M == 0) return 0;
+    for (int i = 0; i < npar; ++i)
+        if (!hp[i]) return fail(ctx, MLM_EINVAL, who);
+    if (!stats || (Tn > 0 && (!flux || !weight))) return fail(ctx, MLM_EINVAL, who);
+    DeviceGuard g(ctx->device);
+    const size_t mpad = ((size_t)M + 31) & ~(size_t)31, tpad = ((size_t)Tn + 31) & ~(size_t)31;
+    int rc = ensure_dbuf(ctx, (mpad * 16 + tpad * 3) * sizeof(double));
+    if (rc) return rc;
+    double* par = (double*)ctx->dbuf;
+    double* dflux = par + 8 * mpad;
+    double* dw = dflux + tpad;
+    double* dtimes = dw + tpad;
+    double* dstats = dtimes + tpad;
+    cudaStream_t st = ctx->stream[0];
+    for (int i = 0; i < npar; ++i) CK(cudaMemcpyAsync(par + i * mpad, hp[i], M * 8, cudaMemcpyHostToDevice, st));
+    if (Tn > 0) {
+        CK(cudaMemcpyAsync(dflux, flux, Tn * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(dw, weight, Tn * 8, cudaMemcpyHostToDevice, st));
+        if (times) CK(cudaMemcpyAsync(dtimes, times, Tn * 8, cudaMemcpyHostToDevice, st));
+    }
+    const Epochs ep = {tau0, dtau, times ? dtimes : nullptr, npar == 8 ? par + 6 * mpad : nullptr,
+                       npar == 8 ? par + 7 * mpad : nullptr};
+    rc = launch_models_chi2(ctx, who, par, par + mpad, par + 2 * mpad, par + 3 * mpad, par + 4 * mpad, par + 5 * mpad, M,
+                            ep, Tn, order, dflux, dw, dstats, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(stats, dstats, (size_t)M * 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     return 0;
 }
 
 int mlm_models_chi2_host(mlm_context* ctx, const double* s, const double* q, const double* rho, const double* Gamma,
                          const double* u0, const double* alpha, int64_t M, double tau0, double dtau, int64_t Tn,
                          int order, const double* flux, const double* weight, double* stats) {
-    if (!ctx) return fail(ctx, MLM_EINVAL, "mlm_models_chi2_host: NULL context");
-    if (M < 0 || Tn < 0 || (order != 2 && order != 4)) return fail(ctx, MLM_EINVAL, "mlm_models_chi2_host: bad argument");
-    if (M == 0) return 0;
-    if (!s || !q || !rho || !Gamma || !u0 || !alpha || !stats || (Tn > 0 && (!flux || !weight)))
-        return fail(ctx, MLM_EINVAL, "mlm_models_chi2_host: NULL buffer");
-    DeviceGuard g(ctx->device);
-    const size_t mpad = ((size_t)M + 31) & ~(size_t)31, tpad = ((size_t)Tn + 31) & ~(size_t)31;
-    int rc = ensure_dbuf(ctx, (mpad * 14 + tpad * 2) * sizeof(double));
-    if (rc) return rc;
-    double* par = (double*)ctx->dbuf;
-    double* dflux = par + 6 * mpad;
-    double* dw = dflux + tpad;
-    double* dstats = dw + tpad;
     const double* hp[6] = {s, q, rho, Gamma, u0, alpha};
-    cudaStream_t st = ctx->stream[0];
-    for (int i = 0; i < 6; ++i) CK(cudaMemcpyAsync(par + i * mpad, hp[i], M * 8, cudaMemcpyHostToDevice, st));
-    if (Tn > 0) {
-        CK(cudaMemcpyAsync(dflux, flux, Tn * 8, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(dw, weight, Tn * 8, cudaMemcpyHostToDevice, st));
-    }
-    rc = mlm_models_chi2(ctx, par, par + mpad, par + 2 * mpad, par + 3 * mpad, par + 4 * mpad, par + 5 * mpad, M, tau0,
-                         dtau, Tn, order, dflux, dw, dstats, st);
-    if (rc) return rc;
-    CK(cudaMemcpyAsync(stats, dstats, (size_t)M * 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    return 0;
+    return models_chi2_host_impl(ctx, "mlm_models_chi2_host: bad argument", hp, 6, M, tau0, dtau, nullptr, Tn, order, flux,
+                                 weight, stats);
+}
+
+int mlm_models_chi2_times_host(mlm_context* ctx, const double* s, const double* q, const double* rho,
+                               const double* Gamma, const double* u0, const double* alpha, const double* t0,
+                               const double* tE, int64_t M, const double* times, int64_t Tn, int order,
+                               const double* flux, const double* weight, double* stats) {
+    if (Tn > 0 && !times) return fail(ctx, MLM_EINVAL, "mlm_models_chi2_times_host: NULL times");
+    const double* hp[8] = {s, q, rho, Gamma, u0, alpha, t0, tE};
+    return models_chi2_host_impl(ctx, "mlm_models_chi2_times_host: bad argument", hp, 8, M, 0.0, 0.0, times, Tn, order,
+                                 flux, weight, stats);
 }
 
 int mlm_from_wk(mlm_context* ctx, const double* Wk, int64_t n, int order, double rho, double Gamma, double* out,
@@ -979,40 +1077,45 @@ int mlm_map_host(mlm_context* ctx, double s, double q, double rho, double Gamma,
     return 0;
 }
 
-int mlm_models_host(mlm_context* ctx, const double* s, const double* q, const double* rho, const double* Gamma,
-                    const double* u0, const double* alpha, int64_t M, double tau0, double dtau, int64_t Tn, int order,
-                    double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags) {
-    if (!ctx) return fail(ctx, MLM_EINVAL, "mlm_models_host: NULL context");
-    if (M < 0 || Tn < 0 || (order != 2 && order != 4)) return fail(ctx, MLM_EINVAL, "mlm_models_host: bad argument");
+static int models_host_impl(mlm_context* ctx, const char* who, const double* const* hp, int npar, int64_t M,
+                            double tau0, double dtau, const double* times, int64_t Tn, int order, double* A0,
+                            double* A2, double* A4, uint8_t* nimg, uint8_t* flags) {
+    if (!ctx) return fail(ctx, MLM_EINVAL, who);
+    if (M < 0 || Tn < 0 || (order != 2 && order != 4)) return fail(ctx, MLM_EINVAL, who);
     if (M == 0 || Tn == 0) return 0;
-    if (!s || !q || !rho || !Gamma || !u0 || !alpha || !(A0 || A2 || A4 || nimg || flags))
-        return fail(ctx, MLM_EINVAL, "mlm_models_host: NULL buffer");
+    for (int i = 0; i < npar; ++i)
+        if (!hp[i]) return fail(ctx, MLM_EINVAL, who);
+    if (!(A0 || A2 || A4 || nimg || flags)) return fail(ctx, MLM_EINVAL, who);
     DeviceGuard g(ctx->device);
     const int64_t n = M * Tn;
     const size_t npad = ((size_t)n + 255) & ~(size_t)255;
-    const size_t mpad = ((size_t)M + 31) & ~(size_t)31;
-    int rc = ensure_dbuf(ctx, npad * 26 + mpad * 48);
+    const size_t mpad = ((size_t)M + 31) & ~(size_t)31, tpad = ((size_t)Tn + 31) & ~(size_t)31;
+    int rc = ensure_dbuf(ctx, npad * 26 + (mpad * 8 + tpad) * 8);
     if (rc) return rc;
     Scratch sc;
     rc = carve(ctx, n, false, &sc);
     if (rc) return rc;
     double* par = (double*)((char*)ctx->dbuf + npad * 26);
-    const double* hp[6] = {s, q, rho, Gamma, u0, alpha};
+    double* dtimes = par + 8 * mpad;
     cudaStream_t st0 = ctx->stream[0];
-    for (int i = 0; i < 6; ++i) CK(cudaMemcpyAsync(par + i * mpad, hp[i], M * 8, cudaMemcpyHostToDevice, st0));
+    for (int i = 0; i < npar; ++i) CK(cudaMemcpyAsync(par + i * mpad, hp[i], M * 8, cudaMemcpyHostToDevice, st0));
+    if (times) CK(cudaMemcpyAsync(dtimes, times, Tn * 8, cudaMemcpyHostToDevice, st0));
     CK(cudaEventRecord(ctx->ev[0], st0));
     CK(cudaStreamWaitEvent(ctx->stream[1], ctx->ev[0], 0));
     int64_t models_per = MLM_CHUNK_POINTS / Tn;
+    if (models_per < (M + 7) / 8) models_per = (M + 7) / 8;          // at most ~8 chunks
     if (models_per < 1) models_per = 1;
     int k = 0;
     for (int64_t m0 = 0; m0 < M; m0 += models_per, ++k) {
         const int64_t nm = (M - m0 < models_per) ? (M - m0) : models_per;
         const int64_t off = m0 * Tn, cnt = nm * Tn;
         cudaStream_t st = ctx->stream[k & 1];
-        rc = mlm_models(ctx, par + m0, par + mpad + m0, par + 2 * mpad + m0, par + 3 * mpad + m0, par + 4 * mpad + m0,
-                        par + 5 * mpad + m0, nm, tau0, dtau, Tn, order, A0 ? sc.A0 + off : nullptr,
-                        A2 ? sc.A2 + off : nullptr, A4 ? sc.A4 + off : nullptr, nimg ? sc.nimg + off : nullptr,
-                        flags ? sc.flags + off : nullptr, st);
+        const Epochs ep = {tau0, dtau, times ? dtimes : nullptr, npar == 8 ? par + 6 * mpad + m0 : nullptr,
+                           npar == 8 ? par + 7 * mpad + m0 : nullptr};
+        rc = launch_models(ctx, who, par + m0, par + mpad + m0, par + 2 * mpad + m0, par + 3 * mpad + m0,
+                           par + 4 * mpad + m0, par + 5 * mpad + m0, nm, ep, Tn, order, A0 ? sc.A0 + off : nullptr,
+                           A2 ? sc.A2 + off : nullptr, A4 ? sc.A4 + off : nullptr, nimg ? sc.nimg + off : nullptr,
+                           flags ? sc.flags + off : nullptr, st);
         if (rc) return rc;
         rc = d2h_chunk(ctx, sc, off, cnt, A0, A2, A4, nimg, flags, st);
         if (rc) return rc;
@@ -1020,6 +1123,24 @@ int mlm_models_host(mlm_context* ctx, const double* s, const double* q, const do
     CK(cudaStreamSynchronize(ctx->stream[0]));
     CK(cudaStreamSynchronize(ctx->stream[1]));
     return 0;
+}
+
+int mlm_models_host(mlm_context* ctx, const double* s, const double* q, const double* rho, const double* Gamma,
+                    const double* u0, const double* alpha, int64_t M, double tau0, double dtau, int64_t Tn, int order,
+                    double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags) {
+    const double* hp[6] = {s, q, rho, Gamma, u0, alpha};
+    return models_host_impl(ctx, "mlm_models_host: bad argument", hp, 6, M, tau0, dtau, nullptr, Tn, order, A0, A2, A4, nimg,
+                            flags);
+}
+
+int mlm_models_times_host(mlm_context* ctx, const double* s, const double* q, const double* rho, const double* Gamma,
+                          const double* u0, const double* alpha, const double* t0, const double* tE, int64_t M,
+                          const double* times, int64_t Tn, int order, double* A0, double* A2, double* A4, uint8_t* nimg,
+                          uint8_t* flags) {
+    if (Tn > 0 && !times) return fail(ctx, MLM_EINVAL, "mlm_models_times_host: NULL times");
+    const double* hp[8] = {s, q, rho, Gamma, u0, alpha, t0, tE};
+    return models_host_impl(ctx, "mlm_models_times_host: bad argument", hp, 8, M, 0.0, 0.0, times, Tn, order, A0, A2, A4,
+                            nimg, flags);
 }
 
 int mlm_from_wk_host(mlm_context* ctx, const double* Wk, int64_t n, int order, double rho, double Gamma, double* out) {

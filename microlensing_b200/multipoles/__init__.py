@@ -5,4 +5,4 @@ from .multipoles import quadrupole, hexadecapole, _akl, _solvelenseq, example  #
 from . import multipoles  # noqa: F401  (microlensing.multipoles.multipoles, the reference's real module path)
 from . import Rkp  # noqa: F401
 from ..batched import (magnification_points, magnification_map, magnification_models, models_chi2,  # noqa: F401
-                       map_coordinates, lightcurve_coordinates, alloc_outputs)
+                       map_coordinates, lightcurve_coordinates, lightcurve_coordinates_at, alloc_outputs)

@@ -283,6 +283,52 @@ def test_models_chi2_fused_fit(mb):
     assert np.allclose(r2["SA"], (w[None, :] * lc["A2"]).sum(axis=1), rtol=1e-10)
 
 
+def test_models_at_observation_times(mb):
+    """Light curves at unevenly spaced observation times with per-model (t0, tE) -- the in-kernel trajectory
+    zeta(t; t0, tE, u0, alpha) of SURVEY.md §8(f).1 -- against the point solver on the same positions and,
+    for the fused fit, against NumPy sums over those light curves."""
+    rng = np.random.default_rng(5)
+    M, T = 12, 900
+    s = np.exp(rng.uniform(np.log(0.6), np.log(1.6), M))
+    q = np.exp(rng.uniform(np.log(1e-3), np.log(1.), M))
+    rho = np.full(M, 1e-3)
+    G = np.full(M, 0.5)
+    u0, al = rng.uniform(-.3, .3, M), rng.uniform(0, 2 * np.pi, M)
+    t0 = 2459000.0 + rng.uniform(-5, 5, M)
+    tE = rng.uniform(15, 60, M)
+    # nightly clusters of exposures with gaps (days), like a ground-based survey
+    nights = 2459000.0 - 40 + np.sort(rng.choice(80, 60, replace=False)).astype(float)
+    times = np.sort(np.concatenate([n + 0.3 + np.sort(rng.uniform(0, 0.3, T // 60)) for n in nights]))
+    T = times.size
+    r = mb.magnification_models(s, q, rho, G, u0, al, times=times, t0=t0, tE=tE)
+    assert r["A4"].shape == (M, T)
+    for m in range(M):
+        zeta = mb.lightcurve_coordinates_at(s[m], q[m], u0[m], al[m], times, t0[m], tE[m])
+        p = mb.magnification_points(s[m], q[m], rho[m], G[m], zeta)
+        assert np.array_equal(p["nimg"], r["nimg"][m]), m
+        ok = (p["flags"] == 0) & (r["flags"][m] == 0)
+        for k in ("A0", "A2", "A4"):
+            assert np.abs(r[k][m] / p[k] - 1)[ok].max() < 1e-9, (m, k)
+    assert ((r["flags"] & 3) == 0).all()
+    # scalar t0 / tE and the default (times already in Einstein times) agree with the uniform-grid kernel
+    tau = -2.0 + 4.0 / 500 * np.arange(500)
+    a = mb.magnification_models(s, q, rho, G, u0, al, times=tau)
+    b = mb.magnification_models(s, q, rho, G, u0, al, -2.0, 4.0 / 500, 500)
+    assert np.array_equal(a["nimg"], b["nimg"])
+    okab = (a["flags"] == 0) & (b["flags"] == 0)
+    assert np.abs(a["A4"] / b["A4"] - 1)[okab].max() < 1e-9
+    # fused fit at observation times
+    sigma = np.full(T, 0.02)
+    flux = 1.5 * r["A4"][3] + 0.2 + sigma * rng.normal(size=T)
+    c = mb.models_chi2(s, q, rho, G, u0, al, flux=flux, sigma=sigma, times=times, t0=t0, tE=tE)
+    w = 1 / sigma ** 2
+    for m in range(M):
+        A = r["A4"][m]
+        assert np.allclose([c["SA"][m], c["SAA"][m], c["SAF"][m]], [(w * A).sum(), (w * A * A).sum(), (w * A * flux).sum()],
+                           rtol=1e-10)
+    assert int(np.argmin(c["chi2"])) == 3 and abs(c["Fs"][3] - 1.5) < 0.05
+
+
 def test_image_count_is_odd_where_the_reference_loses_images(mb):
     """Images almost on top of a lens (very distant source, q <= 1e-5): the reference counts 2, the truth and
     the kernel 3; values equal the 40-digit evaluation."""
