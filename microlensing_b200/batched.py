@@ -13,7 +13,7 @@ import numpy as np
 from . import _capi
 
 __all__ = ["Magnification", "magnification_points", "magnification_map", "magnification_models", "models_chi2",
-           "models_chi2_device",
+           "models_chi2_device", "models_times_device", "models_chi2_times_device",
            "map_coordinates", "lightcurve_coordinates", "lightcurve_coordinates_at", "alloc_outputs", "ALL_OUTPUTS", "map_device", "map_strips_device", "points_device",
            "models_device"]
 
@@ -244,6 +244,23 @@ def models_chi2_device(s, q, rho, Gamma, u0, alpha, M, tau0, dtau, T, flux, weig
     ctx = _capi.context(device)
     ctx.check(ctx.lib.mlm_models_chi2(ctx.handle, _p(s), _p(q), _p(rho), _p(Gamma), _p(u0), _p(alpha), M, tau0, dtau, T,
                                       order, _p(flux), _p(weight), _p(stats), _p(stream)), "mlm_models_chi2")
+
+
+def models_times_device(s, q, rho, Gamma, u0, alpha, t0, tE, M, times, T, A0, A2, A4, nimg=None, flags=None, order=4,
+                        stream=None, device=None):
+    """Model grid at observation times (device arrays; t0 / tE may be None = 0 / 1)."""
+    ctx = _capi.context(device)
+    ctx.check(ctx.lib.mlm_models_times(ctx.handle, _p(s), _p(q), _p(rho), _p(Gamma), _p(u0), _p(alpha), _p(t0), _p(tE), M,
+                                       _p(times), T, order, _p(A0), _p(A2), _p(A4), _p(nimg), _p(flags), _p(stream)),
+              "mlm_models_times")
+
+
+def models_chi2_times_device(s, q, rho, Gamma, u0, alpha, t0, tE, M, times, T, flux, weight, stats, order=4, stream=None,
+                             device=None):
+    ctx = _capi.context(device)
+    ctx.check(ctx.lib.mlm_models_chi2_times(ctx.handle, _p(s), _p(q), _p(rho), _p(Gamma), _p(u0), _p(alpha), _p(t0), _p(tE),
+                                            M, _p(times), T, order, _p(flux), _p(weight), _p(stats), _p(stream)),
+              "mlm_models_chi2_times")
 
 
 def models_device(s, q, rho, Gamma, u0, alpha, M, tau0, dtau, T, A0, A2, A4, nimg=None, flags=None, order=4,

@@ -362,8 +362,8 @@ class ShardedModels:
 
     STAT_KEYS = ("chi2", "Fs", "Fb", "SA", "SAA", "SAF", "n5", "nflag")
 
-    def __init__(self, params, tau0: float, dtau: float, T: int, rank: int = 0, world: int = 1, device=None,
-                 group=None, outputs=None, fit=None):
+    def __init__(self, params, tau0: float = 0.0, dtau: float = 0.0, T: int = 0, rank: int = 0, world: int = 1,
+                 device=None, group=None, outputs=None, fit=None, times=None):
         import numpy as np
         import torch
         import torch.distributed as dist
@@ -371,10 +371,16 @@ class ShardedModels:
         self.torch = torch
         self.rank, self.world, self.group = rank, world, group
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        # epochs: the uniform grid tau0 + t dtau, or observation `times` with params = (..., t0, tE)
+        self.times = None
+        if times is not None:
+            th = np.ascontiguousarray(times, dtype=np.float64).ravel()
+            T = th.size
+            self.times = torch.from_numpy(th).to(self.device)
         self.tau0, self.dtau, self.T = float(tau0), float(dtau), int(T)
-        arrs = [np.ascontiguousarray(np.asarray(a, dtype=np.float64)).ravel() for a in params]   # s,q,rho,Gamma,u0,alpha
-        if len(arrs) != 6 or any(a.size != arrs[0].size for a in arrs):
-            raise ValueError("params = (s, q, rho, Gamma, u0, alpha), arrays of equal length M")
+        arrs = [np.ascontiguousarray(np.asarray(a, dtype=np.float64)).ravel() for a in params]   # s,q,rho,Gamma,u0,alpha[,t0,tE]
+        if len(arrs) != (6 if times is None else 8) or any(a.size != arrs[0].size for a in arrs):
+            raise ValueError("params = (s, q, rho, Gamma, u0, alpha) [+ (t0, tE) with times=], arrays of equal length M")
         self.M = arrs[0].size
         self.lo, self.hi = shard_range(self.M, rank, world)
         self.par = [torch.from_numpy(a[self.lo:self.hi].copy()).to(self.device) for a in arrs]
@@ -429,19 +435,30 @@ class ShardedModels:
     def compute(self, order=4):
         """Enqueue this rank's models on the current stream (results land in rank 0's buffer)."""
         import torch.distributed as dist
-        from .batched import models_device, models_chi2_device
+        from .batched import models_device, models_chi2_device, models_times_device, models_chi2_times_device
         ctx, base, _ = self._buf
         st = self.torch.cuda.current_stream(self.device).cuda_stream
         m = self.hi - self.lo
+        dev = self.device.index
+
+        def run(par, nm, A0, A2, A4, ni, fl):
+            if self.times is None:
+                models_device(*par, nm, self.tau0, self.dtau, self.T, A0, A2, A4, ni, fl, order=order, stream=st, device=dev)
+            else:
+                models_times_device(*par, nm, self.times, self.T, A0, A2, A4, ni, fl, order=order, stream=st, device=dev)
+
         if m:
             if self.fit is not None:
-                models_chi2_device(*self.par, m, self.tau0, self.dtau, self.T, self.fit[0], self.fit[1],
-                                   base + self.lo * 64, order=order, stream=st, device=self.device.index)
+                if self.times is None:
+                    models_chi2_device(*self.par, m, self.tau0, self.dtau, self.T, self.fit[0], self.fit[1],
+                                       base + self.lo * 64, order=order, stream=st, device=dev)
+                else:
+                    models_chi2_times_device(*self.par, m, self.times, self.T, self.fit[0], self.fit[1],
+                                             base + self.lo * 64, order=order, stream=st, device=dev)
             elif self.local is None:
                 ptr = {key: (base + self.layout[key] + self.lo * self.T * item if key in self.outputs else None)
                        for key, item in KEYS}
-                models_device(*self.par, m, self.tau0, self.dtau, self.T, ptr["A0"], ptr["A2"], ptr["A4"], ptr["nimg"],
-                              ptr["flags"], order=order, stream=st, device=self.device.index)
+                run(self.par, m, ptr["A0"], ptr["A2"], ptr["A4"], ptr["nimg"], ptr["flags"])
             else:
                 cur = self.torch.cuda.current_stream(self.device)
                 for c in range(self.nchunks):
@@ -449,8 +466,7 @@ class ShardedModels:
                     if b == a:
                         continue
                     v = {key: (self.local[key][a * self.T:] if key in self.local else None) for key, _ in KEYS}
-                    models_device(*[p[a:b] for p in self.par], b - a, self.tau0, self.dtau, self.T, v["A0"], v["A2"],
-                                  v["A4"], v["nimg"], v["flags"], order=order, stream=st, device=self.device.index)
+                    run([p[a:b] for p in self.par], b - a, v["A0"], v["A2"], v["A4"], v["nimg"], v["flags"])
                     self.comm_stream.wait_stream(cur)
                     for key, item in KEYS:
                         if key in self.local:

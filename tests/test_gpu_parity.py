@@ -555,11 +555,17 @@ def _two_gpu_models_worker(rank, world, port, out_dir):
         sf = ShardedModels(par, -2.0, 4.0 / T, T, rank, world, fit=(flux, sigma))
         sf.compute()
         fit = sf.result_host()
+        par8, times = _model_grid_times()
+        st = ShardedModels(par8, rank=rank, world=world, times=times)
+        st.compute()
+        rt = st.result_host()
         if rank == 0:
-            np.savez(os.path.join(out_dir, "models.npz"), **res, **{"fit_" + k: v for k, v in fit.items()})
+            np.savez(os.path.join(out_dir, "models.npz"), **res, **{"fit_" + k: v for k, v in fit.items()},
+                     times_A4=rt["A4"], times_nimg=rt["nimg"])
         dist.barrier()
         sm.close()
         sf.close()
+        st.close()
     finally:
         dist.destroy_process_group()
 
@@ -573,6 +579,14 @@ def _model_grid_case():
     par = (s, q, rho, np.full(M, 0.5), rng.uniform(-.5, .5, M), rng.uniform(0, 2 * np.pi, M))
     flux = 1.0 + rng.random(T)
     return par, T, flux, np.full(T, 0.05)
+
+
+def _model_grid_times():
+    par, T, _, _ = _model_grid_case()
+    rng = np.random.default_rng(78)
+    M = par[0].size
+    times = np.sort(rng.uniform(-30.0, 30.0, 333))
+    return par + (rng.uniform(-2, 2, M), rng.uniform(15, 40, M)), times
 
 
 def test_sharded_models_single_and_two_gpu(mb, tmp_path):
@@ -594,6 +608,13 @@ def test_sharded_models_single_and_two_gpu(mb, tmp_path):
         assert np.array_equal(res[k], one[k]), k
     for k in ShardedModels.STAT_KEYS:
         assert np.array_equal(fit[k], fit1[k]), k
+    par8, times = _model_grid_times()
+    onet = mb.magnification_models(*par8[:6], times=times, t0=par8[6], tE=par8[7])
+    stt = ShardedModels(par8, times=times)
+    stt.compute()
+    rt = stt.result_host()
+    stt.close()
+    assert np.array_equal(rt["A4"], onet["A4"]) and np.array_equal(rt["nimg"], onet["nimg"])
     if torch.cuda.device_count() < 2:
         return
     import socket
@@ -607,6 +628,7 @@ def test_sharded_models_single_and_two_gpu(mb, tmp_path):
         assert np.array_equal(got[k], one[k]), k
     for k in ShardedModels.STAT_KEYS:
         assert np.array_equal(got["fit_" + k], fit1[k]), k
+    assert np.array_equal(got["times_A4"], onet["A4"]) and np.array_equal(got["times_nimg"], onet["nimg"])
 
 
 def test_full_size_properties(mb):
