@@ -298,3 +298,26 @@ def test_logic_image_count_is_odd_where_the_reference_loses_images(emu):
             assert np.allclose(A[i], t[1:4], rtol=1e-12), (s, q, z)
             ref_wrong += oracle.point_a4(s, q, 1e-3, 0.5, z)[0] != t[0]
     assert ref_wrong > 10          # the regime is indeed one where the reference miscounts
+
+
+def test_bench_reference_arm_line_and_no_gpu_failure():
+    """bench.py --impl reference prints exactly one JSON line with the contract's keys (it needs no GPU:
+    it times the oracle on the host cores); the b200 arm refuses to run without a CUDA device."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--ref-per-core", "200"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-500:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "mags/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
+    assert d["e2e"] == {"value": d["value"], "unit": "mags/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["metric"].startswith("A4 magnifications/sec") and "8192x8192" in d["config"]["workload"]
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0"],
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
