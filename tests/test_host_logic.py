@@ -321,3 +321,29 @@ def test_bench_reference_arm_line_and_no_gpu_failure():
         r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0"],
                            capture_output=True, text=True, timeout=600)
         assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
+
+
+def test_operator_form_follows_from_the_derivation_rules(emu):
+    """mu2 = L mu0 and mu4 = 2 L^2 mu0 with L = mu0 D (mu0 Dbar .).  sympy expands both from the
+    derivation rules alone (tools/derive_operator_form.py, 8 and 71 monomials); the kernel's hand-factored
+    formulas (image_terms_from_W, through the host build) and the reference's (xi, eta) recursion (oracle) must
+    be the same functions of W2..W6."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import derive_operator_form as dof
+    from oracle import cassan_oracle as oracle
+    mu2, mu4 = dof.derive()
+    rng = np.random.default_rng(3)
+    z = rng.normal(size=300) + 1j * rng.normal(size=300)
+    Wk = oracle.wk_table(0.9, 0.3, z, 6)
+    W = {k: Wk[k] for k in range(2, 7)}
+    e2, e4 = dof.evaluate(mu2, W), dof.evaluate(mu4, W)
+    assert np.abs(e2.imag).max() <= 1e-9 * np.abs(e2.real).max()            # the Laplacians are real
+    got = emu.image_terms(Wk[2:7].T, 0)                                     # closed form of the kernel
+    r0, r2, r4 = oracle._per_image(Wk, 5)                                    # reference recursion
+    for a, b, name in ((e2.real, got[:, 1], "mu2 kernel"), (e4.real, got[:, 2], "mu4 kernel"),
+                       (e2.real, r2, "mu2 reference"), (e4.real, r4, "mu4 reference")):
+        rel = np.abs(a / b - 1)
+        # the expanded 71-monomial polynomial cancels heavily next to critical curves: judge by the median,
+        # bound the worst case loosely
+        assert np.median(rel) < 1e-11 and rel.max() < 1e-6, (name, np.median(rel), rel.max())
