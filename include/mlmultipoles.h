@@ -23,7 +23,10 @@
  *  - order = 2 computes A0, A2 (quadrupole, multipoles.py:12-65; A4 output is set to 0),
  *    order = 4 computes A0, A2, A4 (hexadecapole, multipoles.py:67-148);
  *  - any of the per-position outputs A0 / A2 / A4 / nimg / flags may be NULL (not stored, not
- *    copied back); at least one must be given.
+ *    copied back); at least one must be given;
+ *  - threads: a context may be shared by host threads.  Entry points that use the context's own device
+ *    scratch (every *_host function, mlm_from_wk) serialise on a mutex inside the context; the other
+ *    device-pointer entry points only enqueue on the caller's stream and keep no state.
  * There is no CPU fallback anywhere in the library: without a CUDA device mlm_create fails.
  */
 #ifndef MLMULTIPOLES_H
@@ -44,7 +47,13 @@ typedef struct mlm_context mlm_context;
 
 /* per-position flag bits written to `flags` (the reference flags nothing) */
 #define MLM_FLAG_NOCONV 1    /* a root-finder iteration cap was hit */
-#define MLM_FLAG_VIETE 2     /* reserved: sum-of-roots check failed */
+#define MLM_FLAG_EXTRA 2     /* nimg includes image(s) that the reference's plain test |z - conj(W1) - zeta| < 1e-6
+                              * (multipoles.py:183) rejects on this solver's polynomial roots: kept because Newton on the
+                              * lens equation converges from the root (root noise of the quintic at q <~ 1e-3), or found
+                              * directly from the lens equation when an even count showed that an image next to a lens was
+                              * lost.  Bits 6-7 hold how many: nimg - ((flags >> MLM_FLAG_EXTRA_SHIFT) & 3) is the count of the
+                              * plain test.  Carried along while the images are tracked from position to position. */
+#define MLM_FLAG_EXTRA_SHIFT 6
 #define MLM_FLAG_NEARCRIT 4  /* min over images of |1-|W2|^2| < 1e-3 (near a critical curve) */
 #define MLM_FLAG_AMBIG 8     /* a root's lens-equation residual within a decade of 1e-6 (multipoles.py:183) */
 #define MLM_FLAG_SERIES 16   /* |A4-A2| > |A2-A0|: multipole series not converging */
@@ -77,13 +86,21 @@ int mlm_ipc_close(mlm_context* ctx, void* p);
  * peer-mapped buffer (model grids, whose kernel stores are strided and would cross NVLink 8 bytes at a time). */
 int mlm_memcpy_async(mlm_context* ctx, void* dst, const void* src, int64_t bytes, void* stream);
 
-/* rows per warm-start strip of mlm_map (default 64; env MLM_MAP_STRIP at mlm_create) */
-int mlm_map_strip(mlm_context* ctx);
-/* Set it (0 = default 64).  The strip length is a numerical parameter of the map kernel, like a tile
- * size: a shorter strip means more independent work items (better tail behaviour of small launches,
- * e.g. 1/8 of a map per GPU) and more cold root solves (~ +2000/L FP64 instructions per pixel).
- * For a fixed strip length the map is bit-identical under any strip-aligned sharding. */
-int mlm_set_map_strip(mlm_context* ctx, int strip);
+/* 2-D variant (cudaMemcpy2DAsync): `height` rows of `width` bytes, pitches in bytes.  Pushes the strips a rank
+ * owns under a cyclic / weighted deal (equally spaced row blocks of the full map) into the gather root's buffer
+ * with one call per output array. */
+int mlm_memcpy2d_async(mlm_context* ctx, void* dst, int64_t dpitch, const void* src, int64_t spitch, int64_t width,
+                       int64_t height, void* stream);
+/* Page-lock an existing host range (cudaHostRegister, portable) / undo it.  The sharded host API maps ONE
+ * POSIX shared-memory result map into every rank's process; each rank registers the rows it owns and its
+ * D2H copies land directly in the map that rank 0 returns. */
+int mlm_host_register(mlm_context* ctx, void* p, int64_t bytes);
+int mlm_host_unregister(mlm_context* ctx, void* p);
+
+/* Strip length the map entry points choose for strip = 0: a power of two in 16..64 from the size of the launch
+ * (nx x nrows pixels on one GPU, about 12 waves of work items).  Callers that compute ONE map in several calls
+ * (row blocks, several GPUs) evaluate it once for the rows per call and pass the value to every call. */
+int mlm_auto_strip(mlm_context* ctx, int64_t nx, int64_t nrows);
 
 /* ---- the fused path: replaces the per-position body of example(), multipoles.py:181-202
  *      (_solvelenseq :156-165, selection :182-183, Wk :185-201, hexadecapole :67-148) -------- */
@@ -105,23 +122,32 @@ int mlm_points_host(mlm_context* ctx, double s, double q, double rho, double Gam
  *   x = x0 + (c + 0.5) dx,  y = y0 + (r + 0.5) dy          (generated in the kernel),
  * rows [row0, row0 + nrows) of an nx-wide map are written to out[(r - row0) * nx + c]
  * (row-shardable: "... to be computed for all source center positions", multipoles.py:184).
- * Rows are processed in strips of mlm_map_strip() consecutive rows (aligned to absolute row
- * numbers) with warm-started root tracking inside a strip: shards whose row0 is a multiple of
- * the strip length reproduce the unsharded map bit for bit. */
+ * Rows are processed in strips of `strip` consecutive rows (aligned to absolute row numbers) with warm-started
+ * root tracking inside a strip.  `strip` is a numerical parameter like a tile size: a shorter strip means more
+ * independent work items (better tail behaviour of small launches, e.g. 1/8 of a map per GPU) and more cold root
+ * solves (~ +2000/strip FP64 instructions per pixel); results for different strip lengths agree to rounding
+ * (<= 4e-11), for ONE strip length the map is bit-identical under any strip-aligned sharding.  strip = 0 chooses
+ * mlm_auto_strip(nx, nrows) (env MLM_MAP_STRIP, read at mlm_create, overrides that choice: experiments). */
 int mlm_map(mlm_context* ctx, double s, double q, double rho, double Gamma,
-            double x0, double y0, double dx, double dy, int64_t nx, int64_t row0, int64_t nrows, int order,
+            double x0, double y0, double dx, double dy, int64_t nx, int64_t row0, int64_t nrows, int order, int strip,
             double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags, void* stream);
-/* Same, restricted to the strips k = kphase (mod kstep) of the row range (strip k = rows
- * [k L, (k+1) L), L = mlm_map_strip()); rows of other strips are not touched.  Cyclic sharding of a
- * map over GPUs: rank r of N calls it with row0 = 0, nrows = ny, kphase = r, kstep = N and output
- * pointers to the FULL map -- every rank then gets the same mix of cheap and expensive (near-caustic)
- * rows, and the union over ranks is bit-identical to the unsharded map. */
+/* Same, restricted to the strips this caller owns under a DEAL: strip k = rows [k L, (k+1) L), L = strip, belongs
+ * to the call iff (k mod period) is one of sel[0..nsel) (ascending, nsel <= 32); rows of other strips are not
+ * touched.  Sharding a map over GPUs: every rank calls it with row0 = 0, nrows = ny, output pointers to the FULL
+ * map and its own positions of the round -- period = N, sel = {rank} deals the strips cyclically (every rank gets
+ * the same mix of cheap and expensive, near-caustic, rows); unequal nsel gives a weighted deal (the gather root
+ * takes more strips because its results do not cross NVLink).  The union over ranks is bit-identical to the
+ * unsharded map.  mlm_map_strips is the cyclic special case (period = kstep, sel = {kphase}). */
+int mlm_map_deal(mlm_context* ctx, double s, double q, double rho, double Gamma,
+                 double x0, double y0, double dx, double dy, int64_t nx, int64_t row0, int64_t nrows,
+                 int64_t period, int nsel, const int32_t* sel, int order, int strip,
+                 double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags, void* stream);
 int mlm_map_strips(mlm_context* ctx, double s, double q, double rho, double Gamma,
                    double x0, double y0, double dx, double dy, int64_t nx, int64_t row0, int64_t nrows,
-                   int64_t kphase, int64_t kstep, int order,
+                   int64_t kphase, int64_t kstep, int order, int strip,
                    double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags, void* stream);
 int mlm_map_host(mlm_context* ctx, double s, double q, double rho, double Gamma,
-                 double x0, double y0, double dx, double dy, int64_t nx, int64_t row0, int64_t nrows, int order,
+                 double x0, double y0, double dx, double dy, int64_t nx, int64_t row0, int64_t nrows, int order, int strip,
                  double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags);
 
 /* Batched model grid: M models x T epochs.  Model m has (s,q,rho,Gamma,u0,alpha)[m] (device

@@ -25,8 +25,10 @@ SIGNATURES = {
     "mlm_destroy": [_P],
     "mlm_launch_count": [_P, ctypes.POINTER(_L)],
     "mlm_synchronize": [_P],
-    "mlm_map_strip": [_P],
-    "mlm_set_map_strip": [_P, _I],
+    "mlm_auto_strip": [_P, _L, _L],
+    "mlm_host_register": [_P, _P, _L],
+    "mlm_host_unregister": [_P, _P],
+    "mlm_memcpy2d_async": [_P, _P, _L, _P, _L, _L, _L, _P],
     "mlm_alloc_host": [_P, _L, ctypes.POINTER(_P)],
     "mlm_free_host": [_P, _P],
     "mlm_device_alloc": [_P, _L, ctypes.POINTER(_P)],
@@ -37,9 +39,11 @@ SIGNATURES = {
     "mlm_memcpy_async": [_P, _P, _P, _L, _P],
     "mlm_points": [_P, _D, _D, _D, _D, _P, _L, _I, _P, _P, _P, _P, _P, _P],
     "mlm_points_host": [_P, _D, _D, _D, _D, _P, _L, _I, _P, _P, _P, _P, _P],
-    "mlm_map": [_P, _D, _D, _D, _D, _D, _D, _D, _D, _L, _L, _L, _I, _P, _P, _P, _P, _P, _P],
-    "mlm_map_strips": [_P, _D, _D, _D, _D, _D, _D, _D, _D, _L, _L, _L, _L, _L, _I, _P, _P, _P, _P, _P, _P],
-    "mlm_map_host": [_P, _D, _D, _D, _D, _D, _D, _D, _D, _L, _L, _L, _I, _P, _P, _P, _P, _P],
+    "mlm_map": [_P, _D, _D, _D, _D, _D, _D, _D, _D, _L, _L, _L, _I, _I, _P, _P, _P, _P, _P, _P],
+    "mlm_map_deal": [_P, _D, _D, _D, _D, _D, _D, _D, _D, _L, _L, _L, _L, _I, ctypes.POINTER(ctypes.c_int32), _I, _I,
+                     _P, _P, _P, _P, _P, _P],
+    "mlm_map_strips": [_P, _D, _D, _D, _D, _D, _D, _D, _D, _L, _L, _L, _L, _L, _I, _I, _P, _P, _P, _P, _P, _P],
+    "mlm_map_host": [_P, _D, _D, _D, _D, _D, _D, _D, _D, _L, _L, _L, _I, _I, _P, _P, _P, _P, _P],
     "mlm_models": [_P, _P, _P, _P, _P, _P, _P, _L, _D, _D, _L, _I, _P, _P, _P, _P, _P, _P],
     "mlm_models_host": [_P, _P, _P, _P, _P, _P, _P, _L, _D, _D, _L, _I, _P, _P, _P, _P, _P],
     "mlm_models_times": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P, _L, _I, _P, _P, _P, _P, _P, _P],
@@ -127,12 +131,22 @@ class Context:
         self.check(self.lib.mlm_fp64_peak(self.handle, ctypes.byref(v)), "mlm_fp64_peak")
         return float(v.value)
 
-    def map_strip(self) -> int:
-        return int(self.lib.mlm_map_strip(self.handle))
+    def auto_strip(self, nx: int, nrows: int) -> int:
+        """Strip length the map entry points choose for strip=0 on a launch of nx x nrows pixels."""
+        v = int(self.lib.mlm_auto_strip(self.handle, int(nx), int(nrows)))
+        if v <= 0:
+            raise ValueError("mlm_auto_strip: bad argument")
+        return v
 
-    def set_map_strip(self, strip: int):
-        """Rows per warm-start strip of the map kernel (0: default 64)."""
-        self.check(self.lib.mlm_set_map_strip(self.handle, int(strip)), "mlm_set_map_strip")
+    def host_register(self, address: int, nbytes: int):
+        self.check(self.lib.mlm_host_register(self.handle, _P(address), int(nbytes)), "mlm_host_register")
+
+    def host_unregister(self, address: int):
+        self.check(self.lib.mlm_host_unregister(self.handle, _P(address)), "mlm_host_unregister")
+
+    def memcpy2d_async(self, dst: int, dpitch: int, src: int, spitch: int, width: int, height: int, stream: int | None):
+        self.check(self.lib.mlm_memcpy2d_async(self.handle, _P(dst), int(dpitch), _P(src), int(spitch), int(width),
+                                               int(height), _P(stream)), "mlm_memcpy2d_async")
 
     def fp64_probe(self, mode: int, blocks_per_sm: int) -> float:
         v = _D(0.0)

@@ -14,7 +14,7 @@ from . import _capi
 
 __all__ = ["Magnification", "magnification_points", "magnification_map", "magnification_models", "models_chi2",
            "models_chi2_device", "models_times_device", "models_chi2_times_device",
-           "map_coordinates", "lightcurve_coordinates", "lightcurve_coordinates_at", "alloc_outputs", "ALL_OUTPUTS", "map_device", "map_strips_device", "points_device",
+           "map_coordinates", "lightcurve_coordinates", "lightcurve_coordinates_at", "alloc_outputs", "ALL_OUTPUTS", "map_device", "map_strips_device", "map_deal_device", "points_device",
            "models_device"]
 
 
@@ -110,8 +110,8 @@ def magnification_map(s, q, rho, Gamma, x0, y0, dx, dy, nx, ny, row0=0, nrows=No
     sampling); coordinates are generated on the GPU, results land in `out` (nrows, nx).
 
     `strip` = rows a thread tracks before it starts afresh (a numerical parameter like a tile size, see
-    mlm_set_map_strip).  None: chosen from the size of the WHOLE map (sharding.auto_strip(nx, ny): 64 rows
-    for 8192^2, 16 for 4096^2 and smaller), so that row blocks of one map computed by separate calls --
+    mlm_map in include/mlmultipoles.h).  None: chosen from the size of the WHOLE map (sharding.auto_strip(nx, ny):
+    64 rows for 8192^2, 16 for 4096^2 and smaller), so that row blocks of one map computed by separate calls --
     on strip boundaries -- are bit-identical to the map computed at once."""
     import os
     from .sharding import auto_strip
@@ -121,17 +121,10 @@ def magnification_map(s, q, rho, Gamma, x0, y0, dx, dy, nx, ny, row0=0, nrows=No
     if out is None:
         out = alloc_outputs(shape, device, pinned=nrows * nx >= (1 << 16), outputs=outputs)
     _check_out(out, shape)
-    old = ctx.map_strip()
     if strip is None:
-        strip = old if os.environ.get("MLM_MAP_STRIP") else auto_strip(nx, ny)      # the env var pins it (experiments)
-    if strip != old:
-        ctx.set_map_strip(strip)
-    try:
-        ctx.check(ctx.lib.mlm_map_host(ctx.handle, s, q, rho, Gamma, x0, y0, dx, dy, nx, row0, nrows, order,
-                                       *_out_ptrs(out)), "mlm_map_host")
-    finally:
-        if strip != old:
-            ctx.set_map_strip(old)
+        strip = 0 if os.environ.get("MLM_MAP_STRIP") else auto_strip(nx, ny)      # the env var pins it (experiments)
+    ctx.check(ctx.lib.mlm_map_host(ctx.handle, s, q, rho, Gamma, x0, y0, dx, dy, nx, row0, nrows, order, int(strip),
+                                   *_out_ptrs(out)), "mlm_map_host")
     return out
 
 
@@ -225,18 +218,32 @@ def points_device(s, q, rho, Gamma, zeta, n, A0, A2, A4, nimg=None, flags=None, 
 
 
 def map_device(s, q, rho, Gamma, x0, y0, dx, dy, nx, row0, nrows, A0, A2, A4, nimg=None, flags=None, order=4,
-               stream=None, device=None):
+               stream=None, device=None, strip=0):
+    """strip = 0: the library picks it from the size of this launch (mlm_auto_strip(nx, nrows))."""
     ctx = _capi.context(device)
-    ctx.check(ctx.lib.mlm_map(ctx.handle, s, q, rho, Gamma, x0, y0, dx, dy, nx, row0, nrows, order,
+    ctx.check(ctx.lib.mlm_map(ctx.handle, s, q, rho, Gamma, x0, y0, dx, dy, nx, row0, nrows, order, int(strip),
                               _p(A0), _p(A2), _p(A4), _p(nimg), _p(flags), _p(stream)), "mlm_map")
 
 
 def map_strips_device(s, q, rho, Gamma, x0, y0, dx, dy, nx, row0, nrows, kphase, kstep, A0, A2, A4, nimg=None,
-                      flags=None, order=4, stream=None, device=None):
+                      flags=None, order=4, stream=None, device=None, strip=0):
     """Strips k = kphase (mod kstep) of the rows [row0, row0+nrows) only (cyclic sharding over GPUs)."""
     ctx = _capi.context(device)
     ctx.check(ctx.lib.mlm_map_strips(ctx.handle, s, q, rho, Gamma, x0, y0, dx, dy, nx, row0, nrows, kphase, kstep,
-                                     order, _p(A0), _p(A2), _p(A4), _p(nimg), _p(flags), _p(stream)), "mlm_map_strips")
+                                     order, int(strip), _p(A0), _p(A2), _p(A4), _p(nimg), _p(flags), _p(stream)),
+              "mlm_map_strips")
+
+
+def map_deal_device(s, q, rho, Gamma, x0, y0, dx, dy, nx, row0, nrows, period, sel, A0, A2, A4, nimg=None,
+                    flags=None, order=4, stream=None, device=None, strip=0):
+    """Strips whose index modulo `period` is in `sel` (ascending) of the rows [row0, row0+nrows): this caller's
+    share of a cyclic or weighted deal of the map over GPUs (mlm_map_deal)."""
+    import ctypes
+    ctx = _capi.context(device)
+    arr = (ctypes.c_int32 * len(sel))(*[int(v) for v in sel])
+    ctx.check(ctx.lib.mlm_map_deal(ctx.handle, s, q, rho, Gamma, x0, y0, dx, dy, nx, row0, nrows, int(period), len(sel),
+                                   arr, order, int(strip), _p(A0), _p(A2), _p(A4), _p(nimg), _p(flags), _p(stream)),
+              "mlm_map_deal")
 
 
 def models_chi2_device(s, q, rho, Gamma, u0, alpha, M, tau0, dtau, T, flux, weight, stats, order=4, stream=None,

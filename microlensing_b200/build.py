@@ -13,7 +13,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmlmultipoles.so")
 SOURCES = ["mlm_kernels.cu"]
-HEADERS = ["mlm_core.cuh", "mlm_qkl_generated.cuh", os.path.join("..", "..", "include", "mlmultipoles.h")]
+# mlmultipoles.h: the C ABI header.  In the repository csrc/mlmultipoles.h is a link to include/mlmultipoles.h;
+# an installed package carries a copy (package-data), so `python -m microlensing_b200.build` works from a wheel.
+HEADERS = ["mlm_core.cuh", "mlm_qkl_generated.cuh", "mlmultipoles.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xptxas", "-v", "-shared", "-Xcompiler", "-fPIC"]
 
@@ -29,15 +31,23 @@ def is_stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS]
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(HERE, "_version.py"), __file__]
     return any(os.path.getmtime(d) > t for d in deps)
+
+
+def _version() -> str:
+    ns: dict = {}
+    with open(os.path.join(HERE, "_version.py")) as f:
+        exec(f.read(), ns)
+    return ns["__version__"]
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
     """Compile the CUDA library if missing or older than its sources; return its path."""
     if not force and not is_stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-I", CSRC, f'-DMLM_VERSION_STRING="{_version()}"', "-o", LIB] + \
+        [os.path.join(CSRC, s) for s in SOURCES]
     proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     log = proc.stdout + proc.stderr
     with open(os.path.join(HERE, "build_ptxas.log"), "w") as f:

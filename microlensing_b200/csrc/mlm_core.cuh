@@ -215,7 +215,8 @@ MLM_HD void lens_polynomial(const LensTable& T, cd zeta, cd c[6]) {
 #define MLM_NEWTON_TOL2 1e-12
 #ifndef MLM_FLAG_NOCONV          /* same values as include/mlmultipoles.h */
 #define MLM_FLAG_NOCONV 1        /* an iteration cap was hit */
-#define MLM_FLAG_VIETE 2         /* reserved */
+#define MLM_FLAG_EXTRA 2         /* nimg counts image(s) that the plain residual test (multipoles.py:183) rejects */
+#define MLM_FLAG_EXTRA_SHIFT 6   /* ... how many: (flags >> 6) & 3, so that nimg - that = count of the plain test */
 #define MLM_FLAG_NEARCRIT 4      /* min_i |1-|W2_i|^2| < 1e-3 over the physical images */
 #define MLM_FLAG_AMBIG 8         /* a root residual within a decade of the 1e-6 threshold */
 #define MLM_FLAG_SERIES 16       /* |A4-A2| > |A2-A0| : multipole series not converging */
@@ -521,8 +522,9 @@ MLM_HD cd lens_newton(const LensTable& T, cd zeta, cd z, double& dz2, double& d2
 // < 1e-7, converges (root noise of the ill-conditioned quintic at small q, amplified by |W2| up to
 // 1e7).  Afterwards the store holds the physical images first (original order kept within each group).
 // Returns the number of physical images.
-MLM_HD int classify_roots(const LensTable& T, cd zeta, cd* sz, int stride, unsigned& flags) {
+MLM_HD int classify_roots(const LensTable& T, cd zeta, cd* sz, int stride, unsigned& flags, int& extra) {
     unsigned phys_mask = 0;
+    extra = 0;                                        // images counted beyond the plain |residual| < 1e-6 test
     cd zk5[5];
 #pragma unroll 1
     for (int k = 0; k < 5; ++k) {
@@ -567,6 +569,7 @@ MLM_HD int classify_roots(const LensTable& T, cd zeta, cd* sz, int stride, unsig
         if (phys) {
             phys_mask |= 1u << k;
             sz[k * stride] = zk;                      // the polished image
+            if (!(f2 < 1e-12)) ++extra;               // rescued: the reference's test alone would have dropped it
         }
     }
     // A binary lens has 3 or 5 images.  An EVEN count means that an image sitting almost on top of a lens
@@ -619,6 +622,7 @@ MLM_HD int classify_roots(const LensTable& T, cd zeta, cd* sz, int stride, unsig
                 if (dup || knear < 0) continue;
                 sz[knear * stride] = zn;
                 phys_mask |= 1u << knear;
+                ++extra;                                 // restored: no polynomial root passed the plain test for it
             }
         }
     }
@@ -640,6 +644,8 @@ MLM_HD int classify_roots(const LensTable& T, cd zeta, cd* sz, int stride, unsig
 struct TrackState {
     int hist;      // usable earlier positions: 0 cold start, 1 previous roots, 2 linear, 3 quadratic extrapolation
     int nimg;      // physical images = the first nimg entries of the root store
+    int extra;     // of which the last classification accepted beyond the reference's plain residual test
+                   // (Newton rescue, odd-count restoration); carried along while the images are tracked
 };
 
 // One step of a coherent sequence: bring the root store (sz current, szp previous, szpp -- optional --
@@ -732,9 +738,14 @@ MLM_HD void advance_images(const LensTable& T, cd zeta, const cd c[6], cd* sz, c
         st.hist = (deg == 5) ? 1 : 0;
     }
     if (need_classify) {
-        st.nimg = classify_roots(T, zeta, sz, stride, flags);
+        // images that were being TRACKED are at rounding level and pass the plain test whatever the polynomial
+        // roots would have done: a re-classification without a cold solve keeps the earlier tally
+        const int carried = need_cold ? 0 : st.extra;
+        st.nimg = classify_roots(T, zeta, sz, stride, flags, st.extra);
+        if (st.extra < carried) st.extra = carried < st.nimg ? carried : st.nimg;
         if (st.hist > 1) st.hist = 1;                 // the order of the store changed: history is void
     }
+    if (st.extra) flags |= MLM_FLAG_EXTRA | ((unsigned)(st.extra < 3 ? st.extra : 3) << MLM_FLAG_EXTRA_SHIFT);
 }
 
 // A0, A2, A4 of a position from its images (the first nimg entries of the root store):
@@ -781,11 +792,34 @@ MLM_HD PointResult point_magnification(const LensTable& T, const SourceFactors s
     PointResult out;
     out.flags = 0;
     TrackState st;
-    st.hist = 0; st.nimg = 0;
+    st.hist = 0; st.nimg = 0; st.extra = 0;
     lens_polynomial(T, zeta, c);
     advance_images(T, zeta, c, z, z, nullptr, 1, st, out.flags);
     sum_images<ORDER>(T, sf, z, 1, st.nimg, out);
     return out;
+}
+
+// ---------------------------------------------------------------------------------------
+// DEAL of the strips of a map over several launches / GPUs (k_map, mlm_map_deal): the strips are dealt in
+// rounds of `period`; a launch owns the positions sel[0..nsel) of every round.  Its strips, in ascending order,
+// carry the ownership index t = round * nsel + j  <->  strip k = round * period + sel[j].
+// ---------------------------------------------------------------------------------------
+#define MLM_DEAL_MAXSEL 32
+struct Deal {
+    int64_t period;
+    int64_t t0;                  // ownership index of the first owned strip inside the row range of a launch
+    int nsel;
+    int sel[MLM_DEAL_MAXSEL];    // ascending positions inside a round
+};
+
+MLM_HD int64_t deal_strip(const Deal& d, int64_t t) { return (t / d.nsel) * d.period + d.sel[t % d.nsel]; }
+
+// smallest ownership index whose strip is >= k
+MLM_HDI int64_t deal_owned_from(const Deal& d, int64_t k) {
+    const int64_t round = k / d.period, pos = k % d.period;
+    int j = 0;
+    while (j < d.nsel && d.sel[j] < pos) ++j;
+    return round * d.nsel + j;                         // j == nsel: the first strip of the next round
 }
 
 // ---------------------------------------------------------------------------------------

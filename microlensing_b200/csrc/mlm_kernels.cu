@@ -19,7 +19,7 @@
 #include <mutex>
 #include <string>
 
-#include "../../include/mlmultipoles.h"
+#include "mlmultipoles.h"                               /* include/mlmultipoles.h; -I set by build.py */
 #include "mlm_core.cuh"
 #include "mlm_qkl_generated.cuh"
 
@@ -61,7 +61,7 @@ k_points(const __grid_constant__ LensTable T, const SourceFactors sf, const doub
     if (i0 >= n) return;
     const int64_t i1 = (i0 + seg < n) ? i0 + seg : n;
     TrackState st;
-    st.hist = 0; st.nimg = 0;
+    st.hist = 0; st.nimg = 0; st.extra = 0;
     cd zprev = mk(0.0, 0.0), dprev = mk(0.0, 0.0);
     for (int64_t i = i0; i < i1; ++i) {
         const double2 zz = __ldg(zeta + i);
@@ -97,11 +97,16 @@ k_points(const __grid_constant__ LensTable T, const SourceFactors sf, const doub
 // first row is a cold solve (Laguerre + deflation), every further row warm-starts Newton from
 // the roots of the row above (pixel pitch ~2e-4 theta_E) and falls back to the cold solve when
 // the tracking check fails (next to caustics).  Stores are coalesced across the 128 columns.
+//
+// Which strips a launch owns is described by a DEAL: the strips of the map are dealt in rounds of
+// `period` strips, and the launch owns the positions sel[0..nsel) of every round (period = 1, nsel = 1:
+// all strips; period = world, sel = {rank}: cyclic sharding; unequal nsel per rank: weighted sharding,
+// e.g. the gather root takes more strips because its results do not cross NVLink).
 template <int ORDER>
 __global__ void __launch_bounds__(MLM_BLOCK, MLM_MAP_MINBLOCKS)
 k_map(const __grid_constant__ LensTable T, const SourceFactors sf, double x0, double y0, double dx, double dy,
-      double shift, int64_t nx, int64_t row0, int64_t nrows, int strip, int64_t kphase, int64_t kstep,
-      int64_t i_first, int64_t i_count, int64_t i_axis, double* __restrict__ A0,
+      double shift, int64_t nx, int64_t row0, int64_t nrows, int strip, const __grid_constant__ Deal deal,
+      int64_t i_count, int64_t i_axis, double* __restrict__ A0,
       double* __restrict__ A2, double* __restrict__ A4, uint8_t* __restrict__ nimg, uint8_t* __restrict__ flags) {
     // root store of this thread: current and previous roots, [k][thread] so that a warp touches
     // 512 contiguous bytes per k (conflict-free); keeps 20 doubles out of the register file
@@ -114,10 +119,8 @@ k_map(const __grid_constant__ LensTable T, const SourceFactors sf, double x0, do
     // x = x0 + (col + 0.5) dx with two roundings (no FMA), so that host code can reproduce
     // the coordinates bit for bit with the same expression.
     const double x = __dadd_rn(__dadd_rn(x0, __dmul_rn((double)col + 0.5, dx)), -shift);
-    // This launch owns the strips k = kphase + i kstep, i = i_first .. i_first + i_count - 1 (kstep = 1:
-    // every strip of the row range; kstep = world, kphase = rank: cyclic sharding over GPUs, which
-    // balances the load whatever the caustic geometry).
-    // They are visited from the lens axis (y = 0, index i_axis) outwards, alternating sides: the
+    // The owned strips (ownership index t = deal.t0 + ii, ii = 0 .. i_count-1, strip k = (t / nsel) period +
+    // sel[t % nsel]) are visited from the lens axis (y = 0, index i_axis) outwards, alternating sides: the
     // caustics -- the 5-image, i.e. expensive, pixels -- sit on the axis, so the heavy blocks are
     // scheduled first and the tail of the launch is made of cheap ones.  Pure scheduling order:
     // the arithmetic of a strip does not depend on it.
@@ -126,11 +129,11 @@ k_map(const __grid_constant__ LensTable T, const SourceFactors sf, double x0, do
         int64_t ii;
         if (j <= 2 * n_min) ii = (j & 1) ? i_axis + (j + 1) / 2 : i_axis - j / 2;
         else ii = (n_hi > n_lo) ? i_axis + (j - n_min) : i_axis - (j - n_min);
-        const int64_t k = kphase + (i_first + ii) * kstep;
+        const int64_t k = deal_strip(deal, deal.t0 + ii);
         const int64_t ra = (k * strip > row0) ? k * strip : row0;
         const int64_t rb = ((k + 1) * strip < row0 + nrows) ? (k + 1) * strip : row0 + nrows;
         TrackState st;
-        st.hist = 0; st.nimg = 0;
+        st.hist = 0; st.nimg = 0; st.extra = 0;
         for (int64_t r = ra; r < rb; ++r) {
             const double y = __dadd_rn(y0, __dmul_rn((double)r + 0.5, dy));
             const cd zeta = mk(x, y);
@@ -218,7 +221,7 @@ k_models(const double* __restrict__ s, const double* __restrict__ q, const doubl
             const int64_t t0 = sg * seg;
             const int64_t t1 = (t0 + seg < Tn) ? t0 + seg : Tn;
             TrackState st;
-            st.hist = 0; st.nimg = 0;
+            st.hist = 0; st.nimg = 0; st.extra = 0;
             double tau_prev = 0.0, dt_prev = 1.0;
             for (int64_t t = t0; t < t1; ++t) {
                 // compiler barrier: the table is re-read from shared memory where it is used instead of
@@ -282,7 +285,7 @@ k_models_chi2(const double* __restrict__ s, const double* __restrict__ q, const 
             const int64_t t0 = sg * seg;
             const int64_t t1 = (t0 + seg < Tn) ? t0 + seg : Tn;
             TrackState st;
-            st.hist = 0; st.nimg = 0;
+            st.hist = 0; st.nimg = 0; st.extra = 0;
             double tau_prev = 0.0, dt_prev = 1.0;
             for (int64_t t = t0; t < t1; ++t) {
                 asm volatile("" ::: "memory");
@@ -457,7 +460,11 @@ struct mlm_context {
     std::atomic<int64_t> launches{0};
     std::string err;
     int sm_count = 148;
-    int map_strip = 64;                                // rows per warm-start strip of k_map (MLM_MAP_STRIP)
+    int map_strip_env = 0;                             // MLM_MAP_STRIP (experiments): overrides strip = 0 (auto)
+    // Serialises the entry points that use the context's own scratch (every *_host function, mlm_from_wk's
+    // partial sums): two host threads may share a context.  Device-pointer entry points only enqueue on the
+    // caller's stream and touch no context state.
+    std::recursive_mutex mu;
     int points_segment = 0;                            // consecutive list entries per thread of k_points (0: from n; MLM_POINTS_SEGMENT)
     int models_segment = 0;                            // epochs per warm-start segment of k_models (0: from T; MLM_SEGMENT)
 };
@@ -468,8 +475,8 @@ static std::mutex g_mu;
 static int fail(mlm_context* ctx, int code, const char* what) {
     std::string msg = std::string(what);
     if (code > 0) msg += std::string(": ") + cudaGetErrorString((cudaError_t)code);
-    if (ctx) ctx->err = msg;
     std::lock_guard<std::mutex> lk(g_mu);
+    if (ctx) ctx->err = msg;
     g_err = msg;
     return code;
 }
@@ -513,7 +520,10 @@ static bool bad_lens(double s, double q) { return !(s > 0.0) || !(q > 0.0) || !s
 
 extern "C" {
 
-const char* mlm_version(void) { return "microlensing_b200 0.1.0 (sm_100a)"; }
+#ifndef MLM_VERSION_STRING
+#define MLM_VERSION_STRING "0.4.0"                     /* build.py passes the package version */
+#endif
+const char* mlm_version(void) { return "microlensing_b200 " MLM_VERSION_STRING " (sm_100a)"; }
 
 const char* mlm_last_error(mlm_context* ctx) {
     if (ctx) return ctx->err.c_str();
@@ -549,7 +559,7 @@ int mlm_create(int device, mlm_context** out) {
     }
     if (const char* e2 = getenv("MLM_MAP_STRIP")) {
         const int v = atoi(e2);
-        if (v >= 1 && v <= 4096) ctx->map_strip = v;
+        if (v >= 1 && v <= 4096) ctx->map_strip_env = v;
     }
     if (const char* e4 = getenv("MLM_POINTS_SEGMENT")) {
         const int v = atoi(e4);
@@ -584,12 +594,26 @@ int mlm_launch_count(mlm_context* ctx, int64_t* out) {
     return 0;
 }
 
-int mlm_map_strip(mlm_context* ctx) { return ctx ? ctx->map_strip : MLM_EINVAL; }
+// Strip length for a map of nx x nrows pixels on one GPU: power of two in 16..64 that leaves about 12 waves of
+// work items (one item = one column of one strip; sm_count x 16 warps of them are resident).  Measured on the
+// 8192-wide C4 map: a launch of w waves of 64-row strips costs about ceil(w + 0.5) block durations, while a
+// shorter strip costs ~2000/L more FP64 instructions per pixel in cold solves.
+static int auto_strip(int sm_count, int64_t nx, int64_t nrows) {
+    const int64_t resident = (int64_t)sm_count * 16 * 32;
+    int strip = 64;
+    while (strip > 16 && nx * (nrows > 0 ? nrows : 1) / strip < 12 * resident) strip /= 2;
+    return strip;
+}
 
-int mlm_set_map_strip(mlm_context* ctx, int strip) {
-    if (!ctx || strip < 0 || strip > 4096) return fail(ctx, MLM_EINVAL, "mlm_set_map_strip: bad argument");
-    ctx->map_strip = strip ? strip : 64;
-    return 0;
+int mlm_auto_strip(mlm_context* ctx, int64_t nx, int64_t nrows) {
+    if (!ctx || nx < 0 || nrows < 0) return MLM_EINVAL;
+    return auto_strip(ctx->sm_count, nx, nrows);
+}
+
+static int resolve_strip(mlm_context* ctx, int strip, int64_t nx, int64_t nrows) {
+    if (strip > 0) return strip;
+    if (ctx->map_strip_env > 0) return ctx->map_strip_env;
+    return auto_strip(ctx->sm_count, nx, nrows);
 }
 
 int mlm_synchronize(mlm_context* ctx) {
@@ -662,6 +686,31 @@ int mlm_memcpy_async(mlm_context* ctx, void* dst, const void* src, int64_t bytes
     return 0;
 }
 
+int mlm_memcpy2d_async(mlm_context* ctx, void* dst, int64_t dpitch, const void* src, int64_t spitch, int64_t width,
+                       int64_t height, void* stream) {
+    if (!ctx || width < 0 || height < 0 || dpitch < width || spitch < width || ((width > 0 && height > 0) && (!dst || !src)))
+        return fail(ctx, MLM_EINVAL, "mlm_memcpy2d_async: bad argument");
+    if (width == 0 || height == 0) return 0;
+    DeviceGuard g(ctx->device);
+    CK(cudaMemcpy2DAsync(dst, (size_t)dpitch, src, (size_t)spitch, (size_t)width, (size_t)height, cudaMemcpyDefault,
+                         pick(ctx, stream)));
+    return 0;
+}
+
+int mlm_host_register(mlm_context* ctx, void* p, int64_t bytes) {
+    if (!ctx || !p || bytes <= 0) return fail(ctx, MLM_EINVAL, "mlm_host_register: bad argument");
+    DeviceGuard g(ctx->device);
+    CK(cudaHostRegister(p, (size_t)bytes, cudaHostRegisterPortable));
+    return 0;
+}
+
+int mlm_host_unregister(mlm_context* ctx, void* p) {
+    if (!ctx || !p) return fail(ctx, MLM_EINVAL, "mlm_host_unregister: bad argument");
+    DeviceGuard g(ctx->device);
+    CK(cudaHostUnregister(p));
+    return 0;
+}
+
 int mlm_ipc_close(mlm_context* ctx, void* p) {
     if (!ctx) return fail(ctx, MLM_EINVAL, "mlm_ipc_close: NULL context");
     if (!p) return 0;
@@ -698,13 +747,22 @@ int mlm_points(mlm_context* ctx, double s, double q, double rho, double Gamma, c
     return 0;
 }
 
-int mlm_map_strips(mlm_context* ctx, double s, double q, double rho, double Gamma, double x0, double y0, double dx,
-                   double dy, int64_t nx, int64_t row0, int64_t nrows, int64_t kphase, int64_t kstep, int order,
-                   double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags, void* stream) {
+int mlm_map_deal(mlm_context* ctx, double s, double q, double rho, double Gamma, double x0, double y0, double dx,
+                 double dy, int64_t nx, int64_t row0, int64_t nrows, int64_t period, int nsel, const int32_t* sel,
+                 int order, int strip, double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags, void* stream) {
     if (!ctx) return fail(ctx, MLM_EINVAL, "mlm_map: NULL context");
-    if (nx < 0 || nrows < 0 || row0 < 0 || (order != 2 && order != 4) || bad_lens(s, q) || kstep < 1 || kphase < 0 ||
-        kphase >= kstep)
+    if (nx < 0 || nrows < 0 || row0 < 0 || (order != 2 && order != 4) || bad_lens(s, q) || period < 1 || nsel < 1 ||
+        nsel > MLM_DEAL_MAXSEL || nsel > period || !sel || strip < 0 || strip > 4096)
         return fail(ctx, MLM_EINVAL, "mlm_map: bad argument");
+    Deal deal;
+    deal.period = period;
+    deal.nsel = nsel;
+    for (int j = 0; j < MLM_DEAL_MAXSEL; ++j) deal.sel[j] = 0;
+    for (int j = 0; j < nsel; ++j) {
+        if (sel[j] < 0 || sel[j] >= period || (j > 0 && sel[j] <= sel[j - 1]))
+            return fail(ctx, MLM_EINVAL, "mlm_map: sel must be ascending positions inside the period");
+        deal.sel[j] = sel[j];
+    }
     if (nx == 0 || nrows == 0) return 0;
     if (!(A0 || A2 || A4 || nimg || flags)) return fail(ctx, MLM_EINVAL, "mlm_map: NULL buffer");
     DeviceGuard g(ctx->device);
@@ -712,39 +770,53 @@ int mlm_map_strips(mlm_context* ctx, double s, double q, double rho, double Gamm
     make_table(s, q, &T);
     const SourceFactors sf = source_factors(rho, Gamma);
     const double shift = s * q / (1.0 + q);            // multipoles.py:178
-    const int strip = ctx->map_strip;
+    strip = resolve_strip(ctx, strip, nx, nrows);
     const int64_t k_first = row0 / strip, k_last = (row0 + nrows - 1) / strip;
-    // strips of this launch: k = kphase + i kstep within [k_first, k_last]
-    const int64_t kk0 = k_first + (((kphase - k_first) % kstep) + kstep) % kstep;
-    if (kk0 > k_last) return 0;
-    const int64_t i_first = (kk0 - kphase) / kstep, i_count = (k_last - kk0) / kstep + 1;
-    // strip that holds the lens axis y = 0 (row index (0 - y0)/dy - 0.5) -> nearest owned strip
+    auto owned_from = [&](int64_t k) { return deal_owned_from(deal, k); };
+    const int64_t t_first = owned_from(k_first), t_end = owned_from(k_last + 1);
+    const int64_t i_count = t_end - t_first;
+    if (i_count <= 0) return 0;
+    deal.t0 = t_first;
+    // owned strip nearest to the lens axis y = 0 (row index (0 - y0)/dy - 0.5)
     int64_t i_axis = 0;
     {
         const double r_axis = (dy != 0.0) ? (-y0 / dy - 0.5) : 0.0;
-        double ia = std::floor((r_axis / (double)strip - (double)kphase) / (double)kstep + 0.5) - (double)i_first;
-        if (!(ia >= 0.0)) ia = 0.0;                                  // also catches NaN
-        if (ia > (double)(i_count - 1)) ia = (double)(i_count - 1);
-        i_axis = (int64_t)ia;
+        double ka = std::floor(r_axis / (double)strip);
+        if (!(ka >= (double)k_first)) ka = (double)k_first;            // also catches NaN
+        if (ka > (double)k_last) ka = (double)k_last;
+        int64_t ia = owned_from((int64_t)ka) - t_first;
+        if (ia < 0) ia = 0;
+        if (ia > i_count - 1) ia = i_count - 1;
+        i_axis = ia;
     }
     dim3 grid((unsigned)((nx + MLM_BLOCK - 1) / MLM_BLOCK), (unsigned)(i_count < 65535 ? i_count : 65535));
     cudaStream_t st = pick(ctx, stream);
     if (order == 4)
-        k_map<4><<<grid, MLM_BLOCK, 0, st>>>(T, sf, x0, y0, dx, dy, shift, nx, row0, nrows, strip, kphase, kstep, i_first,
-                                              i_count, i_axis, A0, A2, A4, nimg, flags);
+        k_map<4><<<grid, MLM_BLOCK, 0, st>>>(T, sf, x0, y0, dx, dy, shift, nx, row0, nrows, strip, deal, i_count, i_axis,
+                                              A0, A2, A4, nimg, flags);
     else
-        k_map<2><<<grid, MLM_BLOCK, 0, st>>>(T, sf, x0, y0, dx, dy, shift, nx, row0, nrows, strip, kphase, kstep, i_first,
-                                              i_count, i_axis, A0, A2, A4, nimg, flags);
+        k_map<2><<<grid, MLM_BLOCK, 0, st>>>(T, sf, x0, y0, dx, dy, shift, nx, row0, nrows, strip, deal, i_count, i_axis,
+                                              A0, A2, A4, nimg, flags);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;
 }
 
+int mlm_map_strips(mlm_context* ctx, double s, double q, double rho, double Gamma, double x0, double y0, double dx,
+                   double dy, int64_t nx, int64_t row0, int64_t nrows, int64_t kphase, int64_t kstep, int order, int strip,
+                   double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags, void* stream) {
+    if (kstep < 1 || kphase < 0 || kphase >= kstep) return fail(ctx, MLM_EINVAL, "mlm_map_strips: bad argument");
+    const int32_t sel = (int32_t)kphase;
+    return mlm_map_deal(ctx, s, q, rho, Gamma, x0, y0, dx, dy, nx, row0, nrows, kstep, 1, &sel, order, strip, A0, A2, A4,
+                        nimg, flags, stream);
+}
+
 int mlm_map(mlm_context* ctx, double s, double q, double rho, double Gamma, double x0, double y0, double dx,
-            double dy, int64_t nx, int64_t row0, int64_t nrows, int order, double* A0, double* A2, double* A4,
+            double dy, int64_t nx, int64_t row0, int64_t nrows, int order, int strip, double* A0, double* A2, double* A4,
             uint8_t* nimg, uint8_t* flags, void* stream) {
-    return mlm_map_strips(ctx, s, q, rho, Gamma, x0, y0, dx, dy, nx, row0, nrows, 0, 1, order, A0, A2, A4, nimg, flags,
-                          stream);
+    const int32_t sel = 0;
+    return mlm_map_deal(ctx, s, q, rho, Gamma, x0, y0, dx, dy, nx, row0, nrows, 1, 1, &sel, order, strip, A0, A2, A4, nimg,
+                        flags, stream);
 }
 
 static int models_segment(mlm_context* ctx, int64_t Tn);
@@ -848,6 +920,7 @@ static int models_chi2_host_impl(mlm_context* ctx, const char* who, const double
         if (!hp[i]) return fail(ctx, MLM_EINVAL, who);
     if (!stats || (Tn > 0 && (!flux || !weight))) return fail(ctx, MLM_EINVAL, who);
     DeviceGuard g(ctx->device);
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     const size_t mpad = ((size_t)M + 31) & ~(size_t)31, tpad = ((size_t)Tn + 31) & ~(size_t)31;
     int rc = ensure_dbuf(ctx, (mpad * 16 + tpad * 3) * sizeof(double));
     if (rc) return rc;
@@ -897,6 +970,7 @@ int mlm_from_wk(mlm_context* ctx, const double* Wk, int64_t n, int order, double
     if (n < 0 || (order != 2 && order != 4) || !out) return fail(ctx, MLM_EINVAL, "mlm_from_wk: bad argument");
     if (n > 0 && !Wk) return fail(ctx, MLM_EINVAL, "mlm_from_wk: NULL Wk");
     DeviceGuard g(ctx->device);
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     cudaStream_t st = pick(ctx, stream);
     const int nout = order == 4 ? 3 : 2;
     if (n == 0) {                                      // zero images -> zeros
@@ -995,6 +1069,7 @@ int mlm_points_host(mlm_context* ctx, double s, double q, double rho, double Gam
     if (n == 0) return 0;
     if (!zeta || !(A0 || A2 || A4 || nimg || flags)) return fail(ctx, MLM_EINVAL, "mlm_points_host: NULL buffer");
     DeviceGuard g(ctx->device);
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     Scratch sc;
     int rc = carve(ctx, n, true, &sc);
     if (rc) return rc;
@@ -1036,14 +1111,15 @@ int mlm_points_host(mlm_context* ctx, double s, double q, double rho, double Gam
 }
 
 int mlm_map_host(mlm_context* ctx, double s, double q, double rho, double Gamma, double x0, double y0, double dx,
-                 double dy, int64_t nx, int64_t row0, int64_t nrows, int order, double* A0, double* A2, double* A4,
-                 uint8_t* nimg, uint8_t* flags) {
+                 double dy, int64_t nx, int64_t row0, int64_t nrows, int order, int strip, double* A0, double* A2,
+                 double* A4, uint8_t* nimg, uint8_t* flags) {
     if (!ctx) return fail(ctx, MLM_EINVAL, "mlm_map_host: NULL context");
-    if (nx < 0 || nrows < 0 || (order != 2 && order != 4) || bad_lens(s, q))
+    if (nx < 0 || nrows < 0 || (order != 2 && order != 4) || bad_lens(s, q) || strip < 0 || strip > 4096)
         return fail(ctx, MLM_EINVAL, "mlm_map_host: bad argument");
     if (nx == 0 || nrows == 0) return 0;
     if (!(A0 || A2 || A4 || nimg || flags)) return fail(ctx, MLM_EINVAL, "mlm_map_host: NULL buffer");
     DeviceGuard g(ctx->device);
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     const int64_t n = nx * nrows;
     Scratch sc;
     int rc = carve(ctx, n, false, &sc);
@@ -1053,7 +1129,7 @@ int mlm_map_host(mlm_context* ctx, double s, double q, double rho, double Gamma,
     int64_t rows_per = MLM_CHUNK_POINTS / nx;
     if (rows_per < (nrows + 7) / 8) rows_per = (nrows + 7) / 8;
     if (rows_per < 1) rows_per = 1;
-    const int64_t L = ctx->map_strip;
+    const int64_t L = strip = resolve_strip(ctx, strip, nx, nrows);
     rows_per = (rows_per + L - 1) / L * L;
     // the first chunk also takes the partial strip up to the next strip boundary of the absolute row
     // numbering, so that every later chunk starts on one
@@ -1064,7 +1140,7 @@ int mlm_map_host(mlm_context* ctx, double s, double q, double rho, double Gamma,
         if (nr > nrows - r) nr = nrows - r;
         const int64_t off = r * nx, cnt = nr * nx;
         cudaStream_t st = ctx->stream[k & 1];
-        rc = mlm_map(ctx, s, q, rho, Gamma, x0, y0, dx, dy, nx, row0 + r, nr, order, A0 ? sc.A0 + off : nullptr,
+        rc = mlm_map(ctx, s, q, rho, Gamma, x0, y0, dx, dy, nx, row0 + r, nr, order, strip, A0 ? sc.A0 + off : nullptr,
                      A2 ? sc.A2 + off : nullptr, A4 ? sc.A4 + off : nullptr, nimg ? sc.nimg + off : nullptr,
                      flags ? sc.flags + off : nullptr, st);
         if (rc) return rc;
@@ -1087,6 +1163,7 @@ static int models_host_impl(mlm_context* ctx, const char* who, const double* con
         if (!hp[i]) return fail(ctx, MLM_EINVAL, who);
     if (!(A0 || A2 || A4 || nimg || flags)) return fail(ctx, MLM_EINVAL, who);
     DeviceGuard g(ctx->device);
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     const int64_t n = M * Tn;
     const size_t npad = ((size_t)n + 255) & ~(size_t)255;
     const size_t mpad = ((size_t)M + 31) & ~(size_t)31, tpad = ((size_t)Tn + 31) & ~(size_t)31;
@@ -1148,6 +1225,7 @@ int mlm_from_wk_host(mlm_context* ctx, const double* Wk, int64_t n, int order, d
     if (n < 0 || (order != 2 && order != 4) || !out) return fail(ctx, MLM_EINVAL, "mlm_from_wk_host: bad argument");
     if (n > 0 && !Wk) return fail(ctx, MLM_EINVAL, "mlm_from_wk_host: NULL Wk");
     DeviceGuard g(ctx->device);
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     const int nrows = order == 4 ? 7 : 5;              // rows 0..4 or 0..6 (rows 0-1 are skipped below)
     const size_t wbytes = (size_t)(nrows - 2) * n * 16;
     int rc = ensure_dbuf(ctx, (size_t)nrows * n * 16 + 64);
@@ -1170,6 +1248,7 @@ int mlm_solve_host(mlm_context* ctx, double s, double q, const double* zeta, int
     if (n == 0) return 0;
     if (!zeta || !roots) return fail(ctx, MLM_EINVAL, "mlm_solve_host: NULL buffer");
     DeviceGuard g(ctx->device);
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     int rc = ensure_dbuf(ctx, (size_t)n * 96);
     if (rc) return rc;
     cudaStream_t st = ctx->stream[0];
@@ -1189,6 +1268,7 @@ int mlm_akl_host(mlm_context* ctx, const double* mu, const double* W2, const dou
     if (n == 0) return 0;
     if (!mu || !W2 || !Q || !out) return fail(ctx, MLM_EINVAL, "mlm_akl_host: NULL buffer");
     DeviceGuard g(ctx->device);
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     int rc = ensure_dbuf(ctx, (size_t)n * 64);
     if (rc) return rc;
     cudaStream_t st = ctx->stream[0];
@@ -1210,6 +1290,7 @@ int mlm_akl_host(mlm_context* ctx, const double* mu, const double* W2, const dou
 int mlm_fp64_peak(mlm_context* ctx, double* tflops) {
     if (!ctx || !tflops) return fail(ctx, MLM_EINVAL, "mlm_fp64_peak: NULL argument");
     DeviceGuard g(ctx->device);
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     int rc = ensure_dbuf(ctx, 64);
     if (rc) return rc;
     cudaStream_t st = ctx->stream[0];
@@ -1243,6 +1324,7 @@ int mlm_fp64_peak(mlm_context* ctx, double* tflops) {
 int mlm_fp64_probe(mlm_context* ctx, int mode, int blocks_per_sm, double* inst_per_s) {
     if (!ctx || !inst_per_s || mode < 1 || mode > 2 || blocks_per_sm < 1) return fail(ctx, MLM_EINVAL, "mlm_fp64_probe: bad argument");
     DeviceGuard g(ctx->device);
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     int rc = ensure_dbuf(ctx, 256);
     if (rc) return rc;
     cudaStream_t st = ctx->stream[0];

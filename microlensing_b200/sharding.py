@@ -1,17 +1,30 @@
 """Row / model sharding across the GPUs of one box and the final gather.
 
 Every source position is independent (reference multipoles.py:184), so there is no exchange
-step on the data path: maps shard by contiguous row blocks, model grids by contiguous model
-ranges.  The only collective is the final gather of the SoA outputs to rank 0
-(26 B/position: A0, A2, A4 float64 + nimg, flags uint8) over NVLink.  Two implementations:
+step on the data path: maps shard by strips of rows, model grids by contiguous model ranges.
+The only collective is the final gather of the SoA outputs (26 B/position: A0, A2, A4 float64 +
+nimg, flags uint8).  A gather to ONE GPU is bound by that GPU's NVLink ingress (measured on this
+pool: 790 GB/s for bulk peer copies from 7 peers, ~660 GB/s for the map kernel's own peer stores;
+profiles/r2_ceilings_n8.json) -- 26 B x 8192^2 x 7/8 = 1.53 GB per map, 1.9 ms, three times the
+0.76 ms a 1/8 share takes to compute.  Hence
 
+* the strips are DEALT with weights (`deal_rounds`): the gather root owns more strips than its peers,
+  because its own results do not cross NVLink; the root share is chosen so that the root's compute
+  time equals the time its peers' results need to arrive;
 * gather="p2p" (default on CUDA, world > 1): rank 0 owns the full-map output buffers and shares
   them with the other processes (CUDA IPC, mlm_ipc_*); every rank passes pointers into that buffer
   to the map kernel, whose epilogue stores go straight into rank 0's HBM over NVLink while the
   kernel is still computing -- the gather is fused into the kernel, one launch per rank, and a
-  1-element NCCL all-reduce on the compute stream is the completion fence.
-* gather="nccl": each rank computes into a local buffer chunk by chunk and torch.distributed
-  gathers every chunk to rank 0 on a side stream, overlapping the next chunk's kernel (baseline).
+  1-element NCCL all-reduce on the compute stream is the completion fence;
+* gather="bulk": the ranks > 0 compute into local HBM in a few row chunks and push each chunk's strips into
+  rank 0's buffer with 2-D bulk peer copies (copy engines; one call per output array and deal position)
+  while the next chunk computes;
+* gather="nccl": each rank computes a contiguous row block chunk by chunk and torch.distributed
+  gathers every chunk to rank 0 on a side stream (baseline).
+* `SharedHostMap` / `magnification_map_sharded`: the result a user wants on the HOST.  One POSIX
+  shared-memory map is mapped into every rank's process; each rank page-locks the rows it owns
+  (mlm_host_register) and its D2H copies land directly in the map rank 0 returns -- no GPU-side gather, every
+  GPU uses its own PCIe link (ceiling measured on this pool: 95 GB/s aggregate for 8 GPUs, 57 GB/s for one).
 
 torch / torch.distributed are plumbing here (device buffers, streams, NCCL); the arithmetic is
 in libmlmultipoles.so.
@@ -21,13 +34,13 @@ from __future__ import annotations
 from dataclasses import dataclass
 
 __all__ = ["shard_range", "ShardPlan", "plan_map", "full_map_layout", "auto_strip", "BYTES_PER_POSITION", "KEYS", "ShardedMap",
-           "ShardedModels"]
+           "ShardedModels", "deal_rounds", "root_share_model", "owned_strips", "SharedHostMap", "magnification_map_sharded"]
 
 BYTES_PER_POSITION = 26           # 3 x float64 + 2 x uint8
 KEYS = (("A0", 8), ("A2", 8), ("A4", 8), ("nimg", 1), ("flags", 1))     # output arrays and their item sizes
 
 
-MAP_STRIP = 64                    # default rows per warm-start strip of the map kernel (mlm_map_strip)
+MAP_STRIP = 64                    # strip length of the stand-in kernels of the CPU tests
 
 
 def shard_range(n: int, rank: int, world: int, align: int = 1) -> tuple[int, int]:
@@ -74,7 +87,8 @@ def auto_strip(nx: int, rows_per_rank: int, resident_threads: int = 148 * 16 * 3
     one work item = one column of one strip; a B200 keeps 148 SMs x 16 warps of them resident.
     Measured on the 8192-wide C4 map (tools/time_shards2.py): a launch of w waves of 64-row strips
     costs about ceil(w + 0.5) block durations, so 1/2, 1/4, 1/8 of the map run best with 32-, 16-,
-    16-row strips (a shorter strip costs ~2000/L more FP64 instructions per pixel in cold solves)."""
+    16-row strips (a shorter strip costs ~2000/L more FP64 instructions per pixel in cold solves).
+    Same rule as mlm_auto_strip() of the C ABI."""
     strip = 64
     while strip > 16 and nx * max(rows_per_rank, 1) // strip < waves * resident_threads:
         strip //= 2
@@ -91,6 +105,66 @@ def full_map_layout(nx: int, ny: int) -> tuple[dict, int]:
     return out, off
 
 
+# ---- weighted deal of the strips over the ranks ----------------------------------------------------------
+MAX_SEL = 32                      # MLM_DEAL_MAXSEL of the C ABI: positions one rank may own in a round
+
+
+def root_share_model(world: int, bytes_per_position: float, rate: float = 1.1e10, ingress: float = 650e9,
+                     latency_fraction: float = 0.0) -> float:
+    """Share of the map the gather root should compute itself.
+
+    Time of the root = f / rate per position; time for the peers' results to enter the root = (1 - f) x bytes /
+    ingress; the peers compute (1 - f) / (world - 1) each.  The balanced share equalises the first two (never below
+    the equal share 1 / world, never so large that the peers idle while the root still computes).
+    rate = positions/s of one GPU on this map (1.1e10 on the C4 map), ingress = bytes/s into one GPU (measured:
+    profiles/r2_ceilings_n8.json)."""
+    if world <= 1:
+        return 1.0
+    a, b = 1.0 / rate, bytes_per_position / ingress
+    f = (b * (1.0 + latency_fraction)) / (a + b)
+    return min(max(f, 1.0 / world), 0.9)
+
+
+def deal_rounds(world: int, root_share: float | None = None, max_period: int = 64) -> tuple[int, tuple]:
+    """(period, sel) with sel[r] = ascending positions of a round of `period` strips owned by rank r.
+
+    Rank 0 gets `a` positions, every other rank `b`, with a / (a + (world-1) b) as close as possible to `root_share`
+    (None or <= 1/world: the plain cyclic deal, period = world).  The root's positions are spread evenly over the
+    round, the others fill the gaps in rank order, so every rank sees the same mix of cheap and expensive rows."""
+    if world < 1:
+        raise ValueError("world must be >= 1")
+    if world == 1:
+        return 1, ((0,),)
+    if root_share is None or root_share <= 1.0 / world + 1e-9:
+        return world, tuple((r,) for r in range(world))
+    best = None
+    for b in range(1, 9):
+        for a in range(b, MAX_SEL + 1):
+            period = a + (world - 1) * b
+            if period > max_period:
+                break
+            err = abs(a / period - root_share)
+            # the shortest round within 0.02 of the wanted share (short rounds = fine-grained balance), else the closest
+            key = (0, period, err) if err <= 0.02 else (1, err, period)
+            if best is None or key < best[0]:
+                best = (key, a, b, period)
+    _, a, b, period = best
+    # positions of the root: evenly spread (Bresenham); the other positions go to ranks 1.. in turn
+    root_pos = sorted({(i * period) // a for i in range(a)})
+    assert len(root_pos) == a
+    others = [p for p in range(period) if p not in set(root_pos)]
+    sel = [tuple(root_pos)] + [tuple(others[r - 1::world - 1]) for r in range(1, world)]
+    assert all(len(x) == b for x in sel[1:]) and sum(len(x) for x in sel) == period
+    return period, tuple(sel)
+
+
+def owned_strips(ny: int, strip: int, period: int, sel) -> list:
+    """Strip indices (ascending) of an ny-row map owned under (period, sel)."""
+    nstrips = -(-ny // strip)
+    pos = set(sel)
+    return [k for k in range(nstrips) if k % period in pos]
+
+
 class _DevMem:
     """Raw device allocation seen through __cuda_array_interface__ (so torch can view it)."""
 
@@ -99,23 +173,27 @@ class _DevMem:
 
 
 class ShardedMap:
-    """Device-resident, row-sharded magnification map with the gather to rank 0 (module docstring).
+    """Device-resident, strip-sharded magnification map with the gather to rank 0 (module docstring).
 
     `compute()` only enqueues work on the current stream of `device`; after a stream / device
     synchronisation rank 0 holds the whole map (`full_views()` / `assemble_host()`).
     `compute_fn` (default: the CUDA map kernel through the C ABI) and device="cpu" exist so that
     the N > 1 host logic (plan, offsets, chunk loop, gather placement) is testable with gloo.
+
+    layout: "block" = one contiguous, strip-aligned row block per rank; "cyclic" = strip k goes to rank
+    k mod world; "weighted" = `deal_rounds(world, root_share)` (root_share None: `root_share_model` for the
+    gathered bytes per position).  cyclic / weighted need gather "p2p" or "bulk", where every rank addresses the
+    full map.  For a given strip length (`align`) the result is bit-identical for every world size and layout.
     """
 
     def __init__(self, nx: int, ny: int, rank: int = 0, world: int = 1, device=None, nchunks: int | None = None,
                  group=None, align: int | None = None, gather: str | None = None, compute_fn=None,
-                 outputs=None, layout: str | None = None):
+                 outputs=None, layout: str | None = None, root_share: float | None = None, rate_hint: float = 1.1e10):
         import torch
         self.torch = torch
         self.nx, self.ny = nx, ny
         # strip length of the map kernel = alignment of the shards.  None: chosen from the per-rank
-        # size (auto_strip) -- the same function of (nx, ny, world) on every rank.  For a given strip
-        # length the sharded map is bit-identical to the unsharded one (Context.set_map_strip).
+        # size (auto_strip) -- the same function of (nx, ny, world) on every rank.
         if align is None:
             align = auto_strip(nx, -(-ny // world)) if compute_fn is None else MAP_STRIP
         self.align = align
@@ -124,47 +202,64 @@ class ShardedMap:
         self.on_cuda = self.device.type == "cuda"
         if gather is None:
             gather = "none" if world == 1 else ("p2p" if self.on_cuda else "nccl")
-        if gather not in ("none", "p2p", "nccl"):
-            raise ValueError("gather must be 'none', 'p2p' or 'nccl'")
+        if gather not in ("none", "p2p", "bulk", "nccl"):
+            raise ValueError("gather must be 'none', 'p2p', 'bulk' or 'nccl'")
         self.gather = gather
-        # how the strips of the map are dealt to the ranks: "block" = one contiguous, strip-aligned row
-        # block per rank; "cyclic" = strip k goes to rank k mod world (same mix of cheap and expensive
-        # rows on every rank; needs the p2p gather, where every rank addresses the full map)
+        peer = gather in ("p2p", "bulk") and world > 1
         if layout is None:
-            layout = "cyclic" if (gather == "p2p" and world > 1) else "block"
-        if layout not in ("block", "cyclic") or (layout == "cyclic" and world > 1 and gather != "p2p"):
-            raise ValueError("layout must be 'block' or 'cyclic' (cyclic needs gather='p2p')")
+            layout = "weighted" if peer else "block"
+        if layout not in ("block", "cyclic", "weighted") or (layout != "block" and world > 1 and not peer) or \
+                (layout == "block" and gather == "bulk"):
+            raise ValueError("layout must be 'block', 'cyclic' or 'weighted' (the last two need gather='p2p'/'bulk'; "
+                             "'bulk' needs a dealt layout)")
         self.layout = layout
-        if nchunks is None:
-            nchunks = 4 if (world > 1 and gather == "nccl") else 1       # chunks only pipeline the NCCL gather
-        self.plan = plan_map(ny, rank, world, nchunks, align)
-        self.compute_fn = compute_fn
         # subset of the five output arrays that is stored / gathered (None: all); the kernel takes
         # NULL for the others
         self.outputs = tuple(k for k, _ in KEYS) if outputs is None else tuple(outputs)
         if not self.outputs or set(self.outputs) - {k for k, _ in KEYS}:
             raise ValueError("outputs must be a non-empty subset of A0, A2, A4, nimg, flags")
+        self.bytes_per_position = sum(item for k, item in KEYS if k in self.outputs)
+        if layout == "weighted" and root_share is None:
+            root_share = root_share_model(world, self.bytes_per_position, rate=rate_hint,
+                                          ingress=780e9 if gather == "bulk" else 650e9,
+                                          latency_fraction=0.12 if gather == "bulk" else 0.0)
+        self.root_share = root_share if layout == "weighted" else (1.0 / world)
+        self.period, self.sel_all = deal_rounds(world, self.root_share if layout == "weighted" else None)
+        self.sel = self.sel_all[rank]
+        if nchunks is None:
+            nchunks = 4 if (world > 1 and gather in ("nccl", "bulk")) else 1   # chunks only pipeline a separate gather
+        self.nchunks = nchunks
+        self.plan = plan_map(ny, rank, world, nchunks, align)
+        self.compute_fn = compute_fn
         n_slot = self.plan.max_rows * nx
         self.n_slot = n_slot
         self.full = None
         self.comm_stream = None
         self._ipc = None
-        if gather == "p2p" and world > 1 and not self._setup_p2p():
+        self.stage = None
+        if peer and not self._setup_p2p():
             # peer mapping is not available on this box (no NVLink / IPC refused): every rank agreed to
             # fall back to the NCCL gather with contiguous blocks
             import warnings
             warnings.warn("ShardedMap: CUDA IPC peer mapping failed, falling back to gather='nccl'")
             gather = self.gather = "nccl"
             self.layout = "block"
+            peer = False
             self.plan = plan_map(ny, rank, world, 4, align)
             n_slot = self.n_slot = self.plan.max_rows * nx
-        if not (gather == "p2p" and world > 1):
+        if not peer:
             self.local = self._alloc(n_slot)
             if world > 1 and self.on_cuda:
                 with torch.cuda.device(self.device):
                     self.comm_stream = torch.cuda.Stream()
             if world > 1 and rank == 0:
                 self.full = [self._alloc(n_slot) if r else self.local for r in range(world)]
+        elif gather == "bulk" and rank != 0:
+            # local staging of this rank's strips, addressed like the full map (only the owned strips are written)
+            self.stage = {key: torch.empty(nx * ny, dtype=torch.float64 if item == 8 else torch.uint8, device=self.device)
+                          for key, item in KEYS if key in self.outputs}
+            with torch.cuda.device(self.device):
+                self.comm_stream = torch.cuda.Stream()
 
     # ---- buffers ---------------------------------------------------------------------------------
     def _alloc(self, n):
@@ -206,8 +301,9 @@ class ShardedMap:
         n = self.nx * self.ny
         lo = p.row0 * self.nx if self.layout == "block" else 0
         # launch targets: raw addresses of this rank's row window (block layout) or of the whole map
-        # (cyclic layout) inside rank 0's buffer (peer-mapped on ranks > 0, where torch never touches
+        # (dealt layouts) inside rank 0's buffer (peer-mapped on ranks > 0, where torch never touches
         # the memory)
+        self.map_layout = layout
         self.local = {key: base + layout[key] + lo * item for key, item in KEYS}
         self.full_map = None
         if p.rank == 0:
@@ -224,7 +320,7 @@ class ShardedMap:
         import torch.distributed as dist
         ctx, base, owner = self._ipc
         self._ipc = None
-        self.local = self.full_map = None
+        self.local = self.full_map = self.stage = None
         self.torch.cuda.synchronize(self.device)
         if not owner:
             ctx.ipc_close(base)
@@ -233,23 +329,6 @@ class ShardedMap:
             ctx.device_free(base)
 
     # ---- work --------------------------------------------------------------------------------------
-    def _set_strip(self):
-        """Make the context's strip length ours; returns the previous one (restored after the launches
-        are enqueued: the strip is read on the host at launch time)."""
-        if self.compute_fn is not None:
-            return None
-        from . import _capi
-        ctx = _capi.context(self.device.index)
-        old = ctx.map_strip()
-        if old != self.align:
-            ctx.set_map_strip(self.align)
-        return old
-
-    def _restore_strip(self, old):
-        if old is not None and old != self.align:
-            from . import _capi
-            _capi.context(self.device.index).set_map_strip(old)
-
     def _launch(self, s, q, rho, Gamma, x0, y0, dx, dy, row0, nrows, views, order, stream):
         if self.compute_fn is not None:
             self.compute_fn(s, q, rho, Gamma, x0, y0, dx, dy, self.nx, row0, nrows, views, order)
@@ -257,32 +336,43 @@ class ShardedMap:
         from .batched import map_device
         v = {k: (views[k] if k in self.outputs else None) for k, _ in KEYS}
         map_device(s, q, rho, Gamma, x0, y0, dx, dy, self.nx, row0, nrows, v["A0"], v["A2"], v["A4"],
-                   v["nimg"], v["flags"], order=order, stream=stream, device=self.device.index)
+                   v["nimg"], v["flags"], order=order, stream=stream, device=self.device.index, strip=self.align)
 
-    def compute(self, s, q, rho, Gamma, x0, y0, dx, dy, order=4, gather=True):
-        """Enqueue this rank's shard (and the gather to rank 0 when world > 1)."""
-        old = self._set_strip()
-        try:
-            self._compute(s, q, rho, Gamma, x0, y0, dx, dy, order, gather)
-        finally:
-            self._restore_strip(old)
+    def _launch_deal(self, s, q, rho, Gamma, x0, y0, dx, dy, row0, nrows, targets, order, stream):
+        from .batched import map_deal_device
+        v = {k: (targets[k] if k in self.outputs else None) for k, _ in KEYS}
+        map_deal_device(s, q, rho, Gamma, x0, y0, dx, dy, self.nx, row0, nrows, self.period, self.sel, v["A0"], v["A2"],
+                        v["A4"], v["nimg"], v["flags"], order=order, stream=stream, device=self.device.index,
+                        strip=self.align)
 
-    def _compute(self, s, q, rho, Gamma, x0, y0, dx, dy, order, gather):
+    def compute(self, s, q, rho, Gamma, x0, y0, dx, dy, order=4, gather=True, local_only=False):
+        """Enqueue this rank's shard (and the gather to rank 0 when world > 1).
+
+        local_only=True: the same strips are computed but stored into this rank's OWN HBM (a scratch map) --
+        the kernel-only time of the sharded job, nothing crosses NVLink."""
         import torch.distributed as dist
         t = self.torch
         p, nx = self.plan, self.nx
         cur = t.cuda.current_stream(self.device) if self.on_cuda else None
         stream = cur.cuda_stream if cur is not None else None
-        if self.gather == "p2p" and p.world > 1:
-            # one launch; the kernel's stores ARE the gather (peer memory on ranks > 0)
-            if self.layout == "cyclic":
-                from .batched import map_strips_device
-                v = {k: (self.local[k] if k in self.outputs else None) for k, _ in KEYS}
-                map_strips_device(s, q, rho, Gamma, x0, y0, dx, dy, nx, 0, self.ny, p.rank, p.world, v["A0"], v["A2"],
-                                  v["A4"], v["nimg"], v["flags"], order=order, stream=stream,
-                                  device=self.device.index)
-            elif p.nrows:
-                self._launch(s, q, rho, Gamma, x0, y0, dx, dy, p.row0, p.nrows, self.local, order, stream)
+        if self.gather in ("p2p", "bulk") and p.world > 1:
+            if local_only:
+                tgt = self._scratch_targets()
+                if self.layout == "block":
+                    if p.nrows:
+                        self._launch(s, q, rho, Gamma, x0, y0, dx, dy, p.row0, p.nrows,
+                                     {k: tgt[k] + p.row0 * nx * item for k, item in KEYS if k in tgt}, order, stream)
+                else:
+                    self._launch_deal(s, q, rho, Gamma, x0, y0, dx, dy, 0, self.ny, tgt, order, stream)
+                return
+            if self.gather == "bulk" and p.rank != 0:
+                self._compute_bulk(s, q, rho, Gamma, x0, y0, dx, dy, order, cur)
+            elif self.layout == "block":
+                # one launch; the kernel's stores ARE the gather (peer memory on ranks > 0)
+                if p.nrows:
+                    self._launch(s, q, rho, Gamma, x0, y0, dx, dy, p.row0, p.nrows, self.local, order, stream)
+            else:
+                self._launch_deal(s, q, rho, Gamma, x0, y0, dx, dy, 0, self.ny, self.local, order, stream)
             if gather:
                 dist.all_reduce(self._fence, group=self.group)      # stream-ordered completion fence
             return
@@ -296,7 +386,7 @@ class ShardedMap:
                 oc = own * nx
                 self._launch(s, q, rho, Gamma, x0, y0, dx, dy, p.row0 + r_off, own,
                              {k: v[o:o + oc] for k, v in buf.items()}, order, stream)
-            if p.world > 1 and gather and self.gather == "nccl":
+            if p.world > 1 and gather and self.gather == "nccl" and not local_only:
                 if self.comm_stream is not None:
                     self.comm_stream.wait_stream(cur)
                 with (t.cuda.stream(self.comm_stream) if self.comm_stream is not None else _null()):
@@ -304,15 +394,65 @@ class ShardedMap:
                         src = buf[key][o:o + cnt]
                         dst = [self.full[r][key][o:o + cnt] for r in range(p.world)] if p.rank == 0 else None
                         dist.gather(src, dst, dst=0, group=self.group)
-        if p.world > 1 and gather and self.comm_stream is not None:
+        if p.world > 1 and gather and self.comm_stream is not None and not local_only:
             cur.wait_stream(self.comm_stream)
 
+    def _scratch_targets(self):
+        """Full-map-sized LOCAL buffers (allocated on first use) for the kernel-only timing."""
+        if getattr(self, "_scratch", None) is None:
+            t = self.torch
+            src = self.stage if self.stage is not None else None
+            self._scratch = src if src is not None else {
+                key: t.empty(self.nx * self.ny, dtype=t.float64 if item == 8 else t.uint8, device=self.device)
+                for key, item in KEYS if key in self.outputs}
+        return {k: v.data_ptr() for k, v in self._scratch.items()}
+
+    def _compute_bulk(self, s, q, rho, Gamma, x0, y0, dx, dy, order, cur):
+        """Ranks > 0 of gather='bulk': kernel per row chunk into local staging, then 2-D peer copies of the owned
+        strips of that chunk into rank 0's buffer on the copy stream while the next chunk computes."""
+        ctx, base, _ = self._ipc
+        nx, L, P = self.nx, self.align, self.period
+        rows_round = L * P
+        nrounds = -(-self.ny // rows_round)
+        tgt = {k: v.data_ptr() for k, v in self.stage.items()}
+        cs = self.comm_stream
+        for c in range(self.nchunks):
+            ra, rb = shard_range(nrounds, c, self.nchunks)
+            if rb == ra:
+                continue
+            row0, row1 = ra * rows_round, min(rb * rows_round, self.ny)
+            self._launch_deal(s, q, rho, Gamma, x0, y0, dx, dy, row0, row1 - row0, tgt,
+                              order, cur.cuda_stream)
+            cs.wait_stream(cur)
+            for key, item in KEYS:
+                if key not in self.stage:
+                    continue
+                sb = L * nx * item                                  # bytes of one strip of this array
+                for pos in self.sel:
+                    first = row0 + pos * L                          # first row of this position's strip in the chunk
+                    if first >= row1:
+                        continue
+                    # strips first, first + rows_round, ... inside [row0, row1); the last one may be cut by the map end
+                    cnt = (row1 - first + rows_round - 1) // rows_round
+                    last_rows = min(L, self.ny - (first + (cnt - 1) * rows_round))
+                    full_cnt = cnt if last_rows == L else cnt - 1
+                    off = first * nx * item
+                    if full_cnt > 0:
+                        ctx.memcpy2d_async(base + self.map_layout[key] + off, rows_round * nx * item,
+                                           self.stage[key].data_ptr() + off, rows_round * nx * item, sb, full_cnt,
+                                           cs.cuda_stream)
+                    if full_cnt < cnt:
+                        off2 = (first + full_cnt * rows_round) * nx * item
+                        ctx.memcpy_async(base + self.map_layout[key] + off2, self.stage[key].data_ptr() + off2,
+                                         last_rows * nx * item, cs.cuda_stream)
+        cur.wait_stream(cs)
+
     def full_views(self):
-        """Rank 0: {key: (ny, nx) tensor} of the whole map without a copy (p2p / single rank), else None."""
+        """Rank 0: {key: (ny, nx) tensor} of the whole map without a copy (p2p / bulk / single rank), else None."""
         p = self.plan
         if p.rank != 0:
             return None
-        if self.gather == "p2p" and p.world > 1:
+        if self.gather in ("p2p", "bulk") and p.world > 1:
             return {k: v.view(self.ny, self.nx) for k, v in self.full_map.items()}
         if p.world == 1:
             return {k: v[: self.ny * self.nx].view(self.ny, self.nx) for k, v in self.local.items()}
@@ -336,6 +476,116 @@ class ShardedMap:
                 parts.append(src[key][:(hi - lo) * nx].cpu().numpy().reshape(hi - lo, nx))
             out[key] = np.concatenate(parts, axis=0)
         return out
+
+
+# ---- host-resident result of a multi-GPU map ---------------------------------------------------------------
+class SharedHostMap:
+    """ONE (ny, nx) result map in POSIX shared memory, mapped into every rank's process (collective constructor over
+    `group`; any torch.distributed backend).  Rank r owns the strip-aligned row block shard_range(ny, r, world, strip);
+    it page-locks exactly those rows (mlm_host_register) so that mlm_map_host's D2H copies run at PCIe speed straight
+    into the map.  `arrays` are numpy views of the whole map (valid on every rank; rank 0 is the one that returns them)."""
+
+    def __init__(self, nx: int, ny: int, rank: int = 0, world: int = 1, group=None, device=None, outputs=None,
+                 strip: int | None = None, register: bool = True):
+        import mmap
+        import os
+        import numpy as np
+        self.nx, self.ny, self.rank, self.world, self.group = nx, ny, rank, world, group
+        self.outputs = tuple(k for k, _ in KEYS) if outputs is None else tuple(outputs)
+        self.strip = auto_strip(nx, -(-ny // world)) if strip is None else int(strip)
+        self.lo, self.hi = shard_range(ny, rank, world, self.strip)
+        layout, nbytes = {}, 0
+        for key, item in KEYS:
+            if key in self.outputs:
+                layout[key] = nbytes
+                nbytes += (nx * ny * item + 4095) // 4096 * 4096
+        self.layout, self.nbytes = layout, max(nbytes, 4096)
+        box = [None]
+        if rank == 0:
+            self.path = f"/dev/shm/mlm_map_{os.getpid()}_{id(self) & 0xffffff:x}"
+            fd = os.open(self.path, os.O_RDWR | os.O_CREAT | os.O_EXCL, 0o600)
+            os.ftruncate(fd, self.nbytes)
+            box[0] = self.path
+        if world > 1:
+            import torch.distributed as dist
+            dist.broadcast_object_list(box, src=0, group=group)
+        self.path = box[0]
+        if rank != 0:
+            fd = os.open(self.path, os.O_RDWR)
+        self._mm = mmap.mmap(fd, self.nbytes)
+        os.close(fd)
+        raw = np.frombuffer(self._mm, dtype=np.uint8)
+        self._base = raw.ctypes.data
+        self.arrays = {key: raw[layout[key]: layout[key] + nx * ny * item].view(np.float64 if item == 8 else np.uint8)
+                       .reshape(ny, nx) for key, item in KEYS if key in self.outputs}
+        self._registered = []
+        self._ctx = None
+        if register and self.hi > self.lo:
+            from . import _capi
+            self._ctx = _capi.context(device)
+            for key, item in KEYS:
+                if key not in self.outputs:
+                    continue
+                a = self._base + layout[key] + self.lo * nx * item
+                b = self._base + layout[key] + self.hi * nx * item
+                a, b = a // 4096 * 4096, (b + 4095) // 4096 * 4096      # whole pages (first touch happens here)
+                if self._registered and a < self._registered[-1][1]:     # adjacent arrays may share a page
+                    a = self._registered[-1][1]
+                if b > a:
+                    self._ctx.host_register(a, b - a)
+                    self._registered.append((a, b))
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier(group=group)
+        if rank == 0:
+            os.unlink(self.path)           # the mappings keep the memory alive; nothing is left behind in /dev/shm
+
+    def own_rows(self):
+        """{key: (hi-lo, nx) view} of the rows this rank owns."""
+        return {k: v[self.lo:self.hi] for k, v in self.arrays.items()}
+
+    def close(self):
+        if self._mm is None:
+            return
+        for a, _ in self._registered:
+            self._ctx.host_unregister(a)
+        self._registered = []
+        self.arrays = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier(group=self.group)
+        try:
+            self._mm.close()
+        except BufferError:                 # a caller still holds a view: the mapping dies with it
+            pass
+        self._mm = None
+
+
+def magnification_map_sharded(s, q, rho, Gamma, x0, y0, dx, dy, nx, ny, rank=0, world=1, group=None, device=None,
+                              order=4, outputs=None, shared: SharedHostMap | None = None):
+    """The whole nx x ny map on the HOST, computed by `world` ranks (one GPU each; collective call).
+
+    Every rank computes its strip-aligned row block with the host API (mlm_map_host: kernel chunks overlapped with
+    the D2H copies) straight into the shared result map; no data crosses NVLink.  Returns the dict of (ny, nx) numpy
+    arrays on rank 0 (views of the shared map; pass `shared` to reuse one across calls), None elsewhere.  The result
+    is bit-identical to magnification_map(..., strip=shared.strip) on one GPU."""
+    from .batched import magnification_map, Magnification
+    own = shared is None
+    sh = SharedHostMap(nx, ny, rank, world, group=group, device=device, outputs=outputs) if own else shared
+    rows = sh.own_rows()
+    if sh.hi > sh.lo:
+        magnification_map(s, q, rho, Gamma, x0, y0, dx, dy, nx, ny, row0=sh.lo, nrows=sh.hi - sh.lo, order=order,
+                          out=Magnification(rows), device=device, outputs=sh.outputs, strip=sh.strip)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier(group=group)
+    res = Magnification(sh.arrays) if rank == 0 else None
+    if own:
+        keep = sh.arrays
+        sh.close()
+        if rank == 0:
+            res = Magnification({k: v.copy() for k, v in keep.items()})   # the mapping is gone after close()
+    return res
 
 
 class _null:

@@ -194,6 +194,16 @@ def select_images(s, q, zeta, z):
     return z[np.abs(z - W1.conjugate() - zeta) < RESIDUAL_THRESHOLD]
 
 
+def lens_residual(s, q, zeta, z):
+    """|z - conj(W1(z)) - zeta| of candidate roots z (last axis) at positions zeta: the quantity the reference
+    compares with 1e-6; multipoles.py:182-183.  NaN where z sits on a lens, like the reference's 1/0."""
+    z = np.asarray(z, dtype=np.complex128)
+    zeta = np.asarray(zeta, dtype=np.complex128)
+    with np.errstate(all="ignore"):
+        W1 = 1. / (1. + q) * (1. / z + q / (z + s))
+        return np.abs(z - W1.conjugate() - zeta[..., None])
+
+
 def wk_table(s, q, z0, kmax=6):
     """Wk[2..kmax] rows of a (7, n) table; multipoles.py:185-191,197-201.
 

@@ -75,7 +75,7 @@ extern "C" void emu_strip(double s, double q, double rho, double Gamma, const do
     SourceFactors sf = source_factors(rho, Gamma);
     cd z[5], zp[5], zpp[5];
     TrackState st;
-    st.hist = 0; st.nimg = 0;
+    st.hist = 0; st.nimg = 0; st.extra = 0;
     long cold = 0;
     for (long i = 0; i < n; ++i) {
         if (i % strip == 0) st.hist = 0;
@@ -92,4 +92,16 @@ extern "C" void emu_strip(double s, double q, double rho, double Gamma, const do
         nimg[i] = (unsigned char)r.nimg; flags[i] = (unsigned char)r.flags;
     }
     *ncold = cold;
+}
+
+// strips [k_first, k_last] owned under a deal, enumerated exactly like mlm_map_deal + k_map do
+extern "C" long emu_deal_strips(long period, int nsel, const int* sel, long k_first, long k_last, long* out, long cap) {
+    Deal d;
+    d.period = period; d.nsel = nsel; d.t0 = 0;
+    for (int j = 0; j < MLM_DEAL_MAXSEL; ++j) d.sel[j] = j < nsel ? sel[j] : 0;
+    const long t_first = deal_owned_from(d, k_first), t_end = deal_owned_from(d, k_last + 1);
+    d.t0 = t_first;
+    long n = 0;
+    for (long ii = 0; ii < t_end - t_first && n < cap; ++ii) out[n++] = deal_strip(d, d.t0 + ii);
+    return t_end - t_first;
 }

@@ -6,7 +6,12 @@
    converging (|A4-A2| > |A2-A0|), or a reference root residual within a decade of the 1e-6
    selection threshold (image-count ambiguity);
 4. disputed points (masked or not) are adjudicated against the 40-digit evaluation of the same
-   formulae: pass iff image count == truth count and |got-truth| <= max(|ref-truth|, RTOL |truth|).
+   formulae: pass iff image count == truth count and |got-truth| <= max(|ref-truth|, RTOL |truth|);
+5. image-count disputes are ACCOUNTED FOR, not just adjudicated: each one must either carry MLM_FLAG_EXTRA with
+   nimg - ((flags >> 6) & 3) == the reference's count (the kernel kept an image that the plain 1e-6 test of
+   multipoles.py:183 rejects on its own roots), or lie in rule 3's mask (the REFERENCE's root residual is within a
+   decade of its threshold: np.roots' unpolished root fails the test that the kernel's polished root passes);
+   the number of disputes is capped (default 1 % of the sample).
 """
 from __future__ import annotations
 
@@ -23,10 +28,16 @@ def mask_from_reference(ref_A, residuals, minJ):
     return (minJ < 1e-3) | series | amb
 
 
-def compare(got_n, got_A, ref_n, ref_A, mask=None, truth_fn=None, max_adjudicate=400):
+FLAG_EXTRA, FLAG_EXTRA_SHIFT = 2, 6
+
+
+def compare(got_n, got_A, ref_n, ref_A, mask=None, truth_fn=None, max_adjudicate=None, got_flags=None,
+            max_dispute_frac=0.01):
     """Returns a report dict; raises AssertionError on a parity failure.
 
     got_A/ref_A: (n,3) arrays.  truth_fn(i) -> (n_truth, A0, A2, A4) for rule 4 (optional).
+    got_flags: the kernel's flag bytes (rule 5; None skips the accounting of count disputes).
+    max_adjudicate: cap on the number of disputes (default max_dispute_frac of the sample, at least 8).
     """
     got_n = np.asarray(got_n).astype(np.int64).ravel()
     ref_n = np.asarray(ref_n).astype(np.int64).ravel()
@@ -39,11 +50,22 @@ def compare(got_n, got_A, ref_n, ref_A, mask=None, truth_fn=None, max_adjudicate
     bad_v = ~(rel <= RTOL)
     disputed = np.where(bad_n | bad_v)[0]
     unmasked_disputes = int(np.sum((bad_n | bad_v) & ~mask))
+    if max_adjudicate is None:
+        max_adjudicate = max(8, int(np.ceil(max_dispute_frac * n)))
     report = dict(n=n, masked=int(mask.sum()), masked_frac=float(mask.mean()) if n else 0.0,
                   nimg_mismatch=int(bad_n.sum()), rel_gt_tol=int((bad_v & ~bad_n).sum()),
                   unmasked_disputes=unmasked_disputes,
                   max_rel_clean=float(np.nanmax(rel[~(bad_n | bad_v)])) if (~(bad_n | bad_v)).any() else 0.0,
                   adjudicated=0, adjudication_failures=[])
+    if got_flags is not None:
+        fl = np.asarray(got_flags).astype(np.int64).ravel()
+        extra = (fl >> FLAG_EXTRA_SHIFT) & 3
+        by_flag = bad_n & ((fl & FLAG_EXTRA) != 0) & (got_n - extra == ref_n)
+        by_mask = bad_n & ~by_flag & mask
+        report.update(nimg_mismatch_flagged_extra=int(by_flag.sum()), nimg_mismatch_ref_ambiguous=int(by_mask.sum()),
+                      nimg_mismatch_unaccounted=int((bad_n & ~by_flag & ~by_mask).sum()),
+                      flagged_extra=int(((fl & FLAG_EXTRA) != 0).sum()))
+        assert report["nimg_mismatch_unaccounted"] == 0, f"image-count disputes without flag or mask: {report}"
     if len(disputed) == 0:
         return report
     if truth_fn is None:

@@ -91,3 +91,34 @@ def test_full_map_layout_offsets():
         assert pos == layout[key] + nx * ny * item
     layout, nbytes = full_map_layout(3, 5)
     assert [layout[k] for k, _ in KEYS] == [0, 256, 512, 768, 1024] and nbytes == 1280
+
+
+def _shm_worker(rank, world, port, nx, ny, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from microlensing_b200.sharding import SharedHostMap, shard_range
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        sh = SharedHostMap(nx, ny, rank, world, outputs=("A4", "nimg"), strip=8, register=False)
+        assert (sh.lo, sh.hi) == shard_range(ny, rank, world, 8) and set(sh.arrays) == {"A4", "nimg"}
+        assert not os.path.exists(sh.path)                       # unlinked once every rank has mapped it
+        rows = sh.own_rows()
+        r = np.arange(sh.lo, sh.hi)[:, None] * nx + np.arange(nx)[None, :]
+        rows["A4"][...] = r * 0.5
+        rows["nimg"][...] = r % 5
+        dist.barrier()
+        if rank == 0:                                            # rank 0 sees every rank's rows in ITS mapping
+            np.savez(os.path.join(out_dir, "shm.npz"), **{k: v.copy() for k, v in sh.arrays.items()})
+        sh.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shared_host_map_is_one_map_for_all_ranks(tmp_path):
+    """SharedHostMap: the POSIX shared-memory result map of the sharded host API (CPU: without page-locking)."""
+    import torch.multiprocessing as mp
+    nx, ny = 24, 50
+    mp.spawn(_shm_worker, args=(2, _free_port(), nx, ny, str(tmp_path)), nprocs=2, join=True)
+    got = np.load(tmp_path / "shm.npz")
+    base = np.arange(nx * ny).reshape(ny, nx)
+    assert np.array_equal(got["A4"], base * 0.5) and np.array_equal(got["nimg"], (base % 5).astype(np.uint8))
