@@ -44,6 +44,7 @@ typedef struct mlm_context mlm_context;
 #define MLM_OK 0
 #define MLM_EINVAL (-1)   /* bad argument (NULL pointer, order not 2/4, negative size, s<=0, q<=0) */
 #define MLM_ENOMEM (-2)   /* host allocation failed */
+#define MLM_ENOTSUP (-3)  /* not available in this build of the library */
 
 /* per-position flag bits written to `flags` (the reference flags nothing) */
 #define MLM_FLAG_NOCONV 1    /* a root-finder iteration cap was hit */
@@ -232,6 +233,14 @@ int mlm_fp64_probe(mlm_context* ctx, int mode, int blocks_per_sm, double* inst_p
 /* static description of the fused kernel (registers per thread, spill bytes) from
  * cudaFuncGetAttributes: [0]=regs points<4>, [1]=local bytes points<4>, [2]=regs map<4>, [3]=local bytes map<4> */
 int mlm_kernel_info(mlm_context* ctx, int32_t* out, int n);
+/* Event counters (measurement only).  libmlmultipoles_stats.so -- the same sources compiled with -DMLM_STATS, built
+ * next to the product library, loaded by bench.py / tools only -- counts what the tracking kernels execute: source
+ * positions, Laguerre / quintic-Newton / lens-equation-Newton evaluations, cold solves, classifications, images summed
+ * (the MLM_COUNT hooks of csrc/mlm_core.cuh).  mlm_stats_names(): the event names, blank-separated, in order;
+ * mlm_stats_read(): out[2e] = lanes, out[2e+1] = warp-level occurrences of event e since the last reset (synchronises
+ * the device).  The product build counts nothing: mlm_stats_read returns MLM_ENOTSUP. */
+const char* mlm_stats_names(void);
+int mlm_stats_read(mlm_context* ctx, uint64_t* out, int n, int reset);
 
 #ifdef __cplusplus
 }

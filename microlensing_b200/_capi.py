@@ -14,6 +14,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MLM_LIB") or os.path.join(_HERE, "libmlmultipoles.so")   # MLM_LIB: experiments only
+# the same sources with -DMLM_STATS (event counters; measurement only: bench.py, tools/) -- never used by the API
+STATS_LIB_PATH = os.path.join(_HERE, "libmlmultipoles_stats.so")
 
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_u8_p = ctypes.POINTER(ctypes.c_uint8)
@@ -61,10 +63,11 @@ SIGNATURES = {
     "mlm_fp64_peak": [_P, ctypes.POINTER(_D)],
     "mlm_fp64_probe": [_P, _I, _I, ctypes.POINTER(_D)],
     "mlm_kernel_info": [_P, ctypes.POINTER(ctypes.c_int32), _I],
+    "mlm_stats_read": [_P, ctypes.POINTER(ctypes.c_uint64), _I, _I],
 }
-STRING_FUNCS = {"mlm_last_error": [_P], "mlm_version": []}
+STRING_FUNCS = {"mlm_last_error": [_P], "mlm_version": [], "mlm_stats_names": []}
 
-_lib = None
+_libs: dict = {}
 _lock = threading.Lock()
 _contexts: dict = {}
 
@@ -73,17 +76,17 @@ class MlmError(RuntimeError):
     pass
 
 
-def load_library():
-    """dlopen libmlmultipoles.so and declare every prototype.  Raises if it is not built."""
-    global _lib
+def load_library(path: str | None = None):
+    """dlopen libmlmultipoles.so (or the library at `path`) and declare every prototype.  Raises if it is not built."""
+    path = LIB_PATH if path is None else path
     with _lock:
-        if _lib is not None:
-            return _lib
-        if not os.path.exists(LIB_PATH):
+        if path in _libs:
+            return _libs[path]
+        if not os.path.exists(path):
             raise ImportError(
-                f"{LIB_PATH} is not built. Run `python -m microlensing_b200.build` (needs nvcc). "
+                f"{path} is not built. Run `python -m microlensing_b200.build` (needs nvcc). "
                 "microlensing_b200 has no CPU fallback.")
-        lib = ctypes.CDLL(LIB_PATH)
+        lib = ctypes.CDLL(path)
         for name, argtypes in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.argtypes = argtypes
@@ -92,15 +95,15 @@ def load_library():
             fn = getattr(lib, name)
             fn.argtypes = argtypes
             fn.restype = ctypes.c_char_p
-        _lib = lib
+        _libs[path] = lib
         return lib
 
 
 class Context:
     """One mlm_context (device, two streams, scratch) per (process, device)."""
 
-    def __init__(self, device: int):
-        self.lib = load_library()
+    def __init__(self, device: int, lib_path: str | None = None):
+        self.lib = load_library(lib_path)
         self.device = device
         h = _P()
         rc = self.lib.mlm_create(device, ctypes.byref(h))
@@ -153,6 +156,13 @@ class Context:
         self.check(self.lib.mlm_fp64_probe(self.handle, mode, blocks_per_sm, ctypes.byref(v)), "mlm_fp64_probe")
         return float(v.value)
 
+    def stats_read(self, reset: bool = True) -> dict:
+        """Event counters of the -DMLM_STATS build: {event: (lanes, warp-level occurrences)}."""
+        names = self.lib.mlm_stats_names().decode().split()
+        a = (ctypes.c_uint64 * (2 * len(names)))()
+        self.check(self.lib.mlm_stats_read(self.handle, a, 2 * len(names), int(reset)), "mlm_stats_read")
+        return {n: (int(a[2 * i]), int(a[2 * i + 1])) for i, n in enumerate(names)}
+
     def kernel_info(self) -> dict:
         a = (ctypes.c_int32 * 4)()
         self.check(self.lib.mlm_kernel_info(self.handle, a, 4), "mlm_kernel_info")
@@ -202,16 +212,18 @@ def default_device() -> int:
     return 0
 
 
-def context(device: int | None = None) -> Context:
+def context(device: int | None = None, stats: bool = False) -> Context:
+    """The process-wide context of `device`.  stats=True: a context of the counting build (measurement only)."""
     if device is None:
         device = default_device()
+    key = (device, stats)
     with _lock:
-        ctx = _contexts.get(device)
+        ctx = _contexts.get(key)
     if ctx is None:
-        ctx = Context(device)
+        ctx = Context(device, STATS_LIB_PATH if stats else None)
         with _lock:
-            _contexts.setdefault(device, ctx)
-            ctx = _contexts[device]
+            _contexts.setdefault(key, ctx)
+            ctx = _contexts[key]
     return ctx
 
 

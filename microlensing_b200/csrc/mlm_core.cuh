@@ -541,6 +541,7 @@ MLM_HD int classify_roots(const LensTable& T, cd zeta, cd* sz, int stride, unsig
         double lim = phys ? 1e-10 : 1e-14;
 #pragma unroll 1
         for (int it = 0; it < 3; ++it) {
+            MLM_COUNT(classify_newton);
             const cd W2 = rfma(T.alpha[2], csq(r1), scale(T.beta[2], csq(r2)));
             const double iJ = rcp_step(1.0 - norm2(W2));
             const cd dz = scale(-iJ, cjfma(W2, conj(f), f));
@@ -655,6 +656,7 @@ MLM_HD void advance_images(const LensTable& T, cd zeta, const cd c[6], cd* sz, c
                            TrackState& st, unsigned& flags, double ratio = 1.0) {
     bool need_cold = true, need_classify = false;
     cd z[5];
+    //@phase track_extrapolate            (markers: regions of the per-phase instruction table, tools/ncu_phase_table.py)
     if (st.hist >= 1 && !(c[5].x == 0.0 && c[5].y == 0.0)) {
         // start values: previous roots, linear (2 z1 - z2) or quadratic (3 z1 - 3 z2 + z3) extrapolation
 #pragma unroll
@@ -678,6 +680,7 @@ MLM_HD void advance_images(const LensTable& T, cd zeta, const cd c[6], cd* sz, c
             szp[k * stride] = zc;
             z[k] = pred;
         }
+        //@phase track_image_newton
         bool ok = true;
         cd sum = mk(0.0, 0.0);
         double mag = 1.0;
@@ -700,6 +703,7 @@ MLM_HD void advance_images(const LensTable& T, cd zeta, const cd c[6], cd* sz, c
                     lim = 1e-2 * dz2;
                 }
             } else {
+                //@phase track_nonphys_newton
                 // non-physical root: Newton on the quintic, then a look at its lens-equation residual
                 double prev = 1e300;
 #pragma unroll 1
@@ -709,11 +713,14 @@ MLM_HD void advance_images(const LensTable& T, cd zeta, const cd c[6], cd* sz, c
                     if (newton_stop(dz2, prev, zk, T.s)) { conv = true; break; }
                     prev = 0.25 * dz2;
                 }
+                //@phase track_nonphys_check
+                MLM_COUNT(nonphys_checks);
                 const cd zs = mk(zk.x + T.s, zk.y);
                 const cd W1 = rfma(T.alpha[1], crcp(zk), scale(T.beta[1], crcp(zs)));
                 const double f2 = norm2(zk - zeta - conj(W1));
                 if (f2 < 1e-2) need_classify = true;  // it may have turned physical (caustic crossing)
             }
+            //@phase track_vieta
             ok = ok && conv;
             z[k] = zk;
             sum = sum + zk;
@@ -730,7 +737,9 @@ MLM_HD void advance_images(const LensTable& T, cd zeta, const cd c[6], cd* sz, c
             MLM_COUNT(track_fallbacks);
         }
     }
+    //@phase cold_glue
     if (need_cold) {
+        MLM_COUNT(cold_solves);
         const int deg = solve_roots(c, T.s, z, flags);
 #pragma unroll
         for (int k = 0; k < 5; ++k) sz[k * stride] = z[k];
@@ -740,6 +749,7 @@ MLM_HD void advance_images(const LensTable& T, cd zeta, const cd c[6], cd* sz, c
     if (need_classify) {
         // images that were being TRACKED are at rounding level and pass the plain test whatever the polynomial
         // roots would have done: a re-classification without a cold solve keeps the earlier tally
+        MLM_COUNT(classify_calls);
         const int carried = need_cold ? 0 : st.extra;
         st.nimg = classify_roots(T, zeta, sz, stride, flags, st.extra);
         if (st.extra < carried) st.extra = carried < st.nimg ? carried : st.nimg;
@@ -756,7 +766,9 @@ MLM_HD void sum_images(const LensTable& T, const SourceFactors sf, const cd* sz,
     double A0 = 0.0, A2 = 0.0, A4 = 0.0, minJ = 1e300;
     unsigned flags = out.flags;
 #pragma unroll 1
+    //@phase image_wk
     for (int k = 0; k < nimg; ++k) {
+        MLM_COUNT(images);
         const cd zk = sz[k * stride];
         const cd zs = mk(zk.x + T.s, zk.y);
         const cd r1 = crcp(zk), r2 = crcp(zs);
@@ -773,6 +785,7 @@ MLM_HD void sum_images(const LensTable& T, const SourceFactors sf, const cd* sz,
             W5 = rfma(T.alpha[5], a5, scale(T.beta[5], b5));
             W6 = rfma(T.alpha[6], a6, scale(T.beta[6], b6));
         }
+        //@phase image_sums
         const ImageTerms t = image_terms_from_W<ORDER>(W2, W3, W4, W5, W6);
         const double v2 = fma(sf.h2, t.mu2, t.mu0);
         A0 += fabs(t.mu0);

@@ -20,6 +20,33 @@
 #include <string>
 
 #include "mlmultipoles.h"                               /* include/mlmultipoles.h; -I set by build.py */
+
+// -DMLM_STATS (libmlmultipoles_stats.so, built next to the product library and used ONLY by bench.py / tools to
+// count what a kernel executes): every MLM_COUNT(event) of mlm_core.cuh adds the number of active lanes to
+// g_mlm_cnt[0][event] and 1 to g_mlm_cnt[1][event] (one atomic pair per warp-level event).
+#define MLM_CNT_NAMES(X) X(positions) X(laguerre_evals) X(newton_evals) X(lens_evals) X(track_fallbacks) X(cold_solves) \
+    X(classify_calls) X(classify_newton) X(nonphys_checks) X(images)
+enum {
+#define X(n) MLM_CNT_##n,
+    MLM_CNT_NAMES(X)
+#undef X
+    MLM_CNT_N
+};
+#ifdef MLM_STATS
+__device__ unsigned long long g_mlm_cnt[2][MLM_CNT_N];
+__host__ __device__ __forceinline__ void mlm_count(int idx) {
+#if defined(__CUDA_ARCH__)
+    const unsigned m = __activemask();
+    if ((int)(threadIdx.x & 31) == __ffs(m) - 1) {
+        atomicAdd(&g_mlm_cnt[0][idx], (unsigned long long)__popc(m));
+        atomicAdd(&g_mlm_cnt[1][idx], 1ULL);
+    }
+#else
+    (void)idx;
+#endif
+}
+#define MLM_COUNT(name) mlm_count(MLM_CNT_##name)
+#endif
 #include "mlm_core.cuh"
 #include "mlm_qkl_generated.cuh"
 
@@ -81,6 +108,7 @@ k_points(const __grid_constant__ LensTable T, const SourceFactors sf, const doub
         cd c[6];
         PointResult r;
         r.flags = 0;
+        MLM_COUNT(positions);
         lens_polynomial(T, zt, c);
         advance_images(T, zt, c, sz, szp, nullptr, MLM_BLOCK, st, r.flags, ratio);
         sum_images<ORDER>(T, sf, sz, MLM_BLOCK, st.nimg, r);
@@ -140,6 +168,7 @@ k_map(const __grid_constant__ LensTable T, const SourceFactors sf, double x0, do
             cd c[6];
             PointResult res;
             res.flags = 0;
+            MLM_COUNT(positions);
             lens_polynomial(T, zeta, c);
             advance_images(T, zeta, c, sz, szp, szpp, MLM_BLOCK, st, res.flags);
             sum_images<ORDER>(T, sf, sz, MLM_BLOCK, st.nimg, res);
@@ -236,6 +265,7 @@ k_models(const double* __restrict__ s, const double* __restrict__ q, const doubl
                 cd c[6];
                 PointResult res;
                 res.flags = 0;
+                MLM_COUNT(positions);
                 lens_polynomial(T, zeta, c);
                 advance_images(T, zeta, c, sz, szp, szpp, MLM_MODELS_BLOCK, st, res.flags, ratio);
                 sum_images<ORDER>(T, sf, sz, MLM_MODELS_BLOCK, st.nimg, res);
@@ -297,6 +327,7 @@ k_models_chi2(const double* __restrict__ s, const double* __restrict__ q, const 
                 cd c[6];
                 PointResult res;
                 res.flags = 0;
+                MLM_COUNT(positions);
                 lens_polynomial(T, zeta, c);
                 advance_images(T, zeta, c, sz, szp, szpp, MLM_MODELS_BLOCK, st, res.flags, ratio);
                 sum_images<ORDER>(T, sf, sz, MLM_MODELS_BLOCK, st.nimg, res);
@@ -1354,6 +1385,33 @@ int mlm_fp64_probe(mlm_context* ctx, int mode, int blocks_per_sm, double* inst_p
     CK(cudaGetLastError());
     *inst_per_s = best;
     return 0;
+}
+
+// Event counters of the -DMLM_STATS build: out[2 * e] = lanes, out[2 * e + 1] = warp-level occurrences of event e
+// (order: mlm_stats_names()); the product build has no counters and answers MLM_ENOTSUP.
+const char* mlm_stats_names(void) {
+#define X(n) #n " "
+    return MLM_CNT_NAMES(X);
+#undef X
+}
+
+int mlm_stats_read(mlm_context* ctx, uint64_t* out, int n, int reset) {
+    if (!ctx || !out || n < 2 * MLM_CNT_N) return fail(ctx, MLM_EINVAL, "mlm_stats_read: bad argument");
+#ifdef MLM_STATS
+    DeviceGuard g(ctx->device);
+    CK(cudaDeviceSynchronize());
+    unsigned long long h[2][MLM_CNT_N];
+    CK(cudaMemcpyFromSymbol(h, g_mlm_cnt, sizeof(h)));
+    for (int e = 0; e < MLM_CNT_N; ++e) { out[2 * e] = h[0][e]; out[2 * e + 1] = h[1][e]; }
+    if (reset) {
+        memset(h, 0, sizeof(h));
+        CK(cudaMemcpyToSymbol(g_mlm_cnt, h, sizeof(h)));
+    }
+    return 0;
+#else
+    (void)reset;
+    return fail(ctx, MLM_ENOTSUP, "mlm_stats_read: this is the product build (counters exist in libmlmultipoles_stats.so only)");
+#endif
 }
 
 int mlm_kernel_info(mlm_context* ctx, int32_t* out, int n) {

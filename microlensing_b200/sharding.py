@@ -421,7 +421,9 @@ class ShardedMap:
             if rb == ra:
                 continue
             row0, row1 = ra * rows_round, min(rb * rows_round, self.ny)
-            self._launch_deal(s, q, rho, Gamma, x0, y0, dx, dy, row0, row1 - row0, tgt,
+            # the kernel addresses its outputs relative to the first row of the launch
+            win = {k: v + row0 * nx * item for k, item in KEYS if (v := tgt.get(k)) is not None}
+            self._launch_deal(s, q, rho, Gamma, x0, y0, dx, dy, row0, row1 - row0, win,
                               order, cur.cuda_stream)
             cs.wait_stream(cur)
             for key, item in KEYS:

@@ -535,6 +535,15 @@ def _two_gpu_worker(rank, world, port, gather, layout, out_dir):
         if layout == "weighted":
             assert sm.period == 5 and len(sm.sel_all[0]) == 3
         sm.compute(s, q, rho, G, x0, y0, dx, dy, local_only=True)     # kernel-only leg: must not disturb the result
+        torch.cuda.synchronize()
+        if sm.stage is not None:                  # poison the staging map: what reaches rank 0 must come from THIS run
+            for v in sm.stage.values():
+                v.fill_(float("nan") if v.dtype == torch.float64 else 255)
+        if rank == 0 and getattr(sm, "full_map", None) is not None:
+            for v in sm.full_map.values():
+                v.fill_(float("nan") if v.dtype == torch.float64 else 255)
+        torch.cuda.synchronize()
+        dist.barrier()
         for _ in range(2):
             sm.compute(s, q, rho, G, x0, y0, dx, dy)
         torch.cuda.synchronize()
