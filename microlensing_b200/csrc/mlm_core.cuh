@@ -198,6 +198,19 @@ MLM_HD void lens_polynomial(const LensTable& T, cd zeta, cd c[6]) {
     c[0] = scale(T.k00, zeta);
 }
 
+// c0, c4, c5 only (same arithmetic as lens_polynomial): what the tracking path needs for the sum and the product
+// of the five roots
+MLM_HD void lens_polynomial_c045(const LensTable& T, cd zeta, cd& c0, cd& c4, cd& c5) {
+    const cd zb = conj(zeta);
+    const double n = norm2(zeta);
+    const cd szb = mk(T.s + zb.x, zb.y);
+    c5 = scale(T.m2, cmul(zb, szb));
+    const cd in = mk(fma(T.k43, zb.x, T.k42 - n), T.k43 * zb.y);
+    const cd t = scale(T.m2, cmul(zb, in));
+    c4 = mk(t.x + fma(T.k41, n, T.k40), t.y);
+    c0 = scale(T.k00, zeta);
+}
+
 // ---------------------------------------------------------------------------------------
 // (b) root finder
 // ---------------------------------------------------------------------------------------
@@ -650,35 +663,49 @@ struct TrackState {
 };
 
 // One step of a coherent sequence: bring the root store (sz current, szp previous, szpp -- optional --
-// the one before; [k * stride], shared memory in the kernels) to the source position zeta with
-// polynomial c.  `ratio` = (this source step) / (previous one) for unevenly spaced sequences.
-MLM_HD void advance_images(const LensTable& T, cd zeta, const cd c[6], cd* sz, cd* szp, cd* szpp, int stride,
+// the one before; [k * stride], shared memory in the kernels) to the source position zeta.
+// `ratio` = (this source step) / (previous one) for unevenly spaced sequences.
+//
+// Three images (the common state): only the images are carried (Newton on the lens equation); the other two roots
+// of the quintic follow from the images by Vieta -- sum of the five roots = -c4/c5, product = -c0/c5 -- as the roots
+// of a quadratic, afresh at every position, and are only looked at: a lens-equation residual below 0.1 means that
+// they are about to turn physical (caustic crossing), then they are polished on the quintic and the position is
+// re-classified.  Only c0, c4, c5 of the polynomial are needed for that; the full polynomial is formed on the rare
+// paths (polish, cold solve) and in the other states (five images: Vieta check of the five tracks; 1, 2 or 4
+// images -- degenerate positions: non-physical roots carried by Newton on the quintic).
+MLM_HD void advance_images(const LensTable& T, cd zeta, cd* sz, cd* szp, cd* szpp, int stride,
                            TrackState& st, unsigned& flags, double ratio = 1.0) {
     bool need_cold = true, need_classify = false;
     cd z[5];
+    cd c0, c4, c5;
+    lens_polynomial_c045(T, zeta, c0, c4, c5);
     //@phase track_extrapolate            (markers: regions of the per-phase instruction table, tools/ncu_phase_table.py)
-    if (st.hist >= 1 && !(c[5].x == 0.0 && c[5].y == 0.0)) {
+    if (st.hist >= 1 && !(c5.x == 0.0 && c5.y == 0.0)) {
+        const bool three = (st.nimg == 3);
+        const int ncarried = three ? 3 : 5;           // roots that are iterated from their predecessors
         // start values: previous roots, linear (2 z1 - z2) or quadratic (3 z1 - 3 z2 + z3) extrapolation
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
-            const cd zc = sz[k * stride];
-            cd pred = zc;
-            if (st.hist >= 2) {
-                const cd zo = szp[k * stride];
-                if (ratio == 1.0) {
-                    if (szpp != nullptr && st.hist >= 3) {
-                        const cd zoo = szpp[k * stride];
-                        pred = mk(fma(3.0, zc.x - zo.x, zoo.x), fma(3.0, zc.y - zo.y, zoo.y));
+            if (k < ncarried) {
+                const cd zc = sz[k * stride];
+                cd pred = zc;
+                if (st.hist >= 2) {
+                    const cd zo = szp[k * stride];
+                    if (ratio == 1.0) {
+                        if (szpp != nullptr && st.hist >= 3) {
+                            const cd zoo = szpp[k * stride];
+                            pred = mk(fma(3.0, zc.x - zo.x, zoo.x), fma(3.0, zc.y - zo.y, zoo.y));
+                        } else {
+                            pred = mk(fma(2.0, zc.x, -zo.x), fma(2.0, zc.y, -zo.y));
+                        }
                     } else {
-                        pred = mk(fma(2.0, zc.x, -zo.x), fma(2.0, zc.y, -zo.y));
+                        pred = mk(fma(ratio, zc.x - zo.x, zc.x), fma(ratio, zc.y - zo.y, zc.y));
                     }
-                } else {
-                    pred = mk(fma(ratio, zc.x - zo.x, zc.x), fma(ratio, zc.y - zo.y, zc.y));
+                    if (szpp != nullptr) szpp[k * stride] = zo;
                 }
-                if (szpp != nullptr) szpp[k * stride] = zo;
+                szp[k * stride] = zc;
+                z[k] = pred;
             }
-            szp[k * stride] = zc;
-            z[k] = pred;
         }
         //@phase track_image_newton
         bool ok = true;
@@ -686,11 +713,11 @@ MLM_HD void advance_images(const LensTable& T, cd zeta, const cd c[6], cd* sz, c
         double mag = 1.0;
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
-            cd zk = z[k];
-            bool conv = false;
             if (k < st.nimg) {
                 // physical image: Newton on the lens equation.  A step below 1e-7 d leaves an error of
                 // ~ (1e-7 d)^2 / d = 1e-14 d: done; every further step must contract by >= 10.
+                cd zk = z[k];
+                bool conv = false;
                 double lim = 1e300;
 #pragma unroll 1
                 for (int it = 0; it < 4; ++it) {
@@ -702,9 +729,68 @@ MLM_HD void advance_images(const LensTable& T, cd zeta, const cd c[6], cd* sz, c
                     if (dz2 <= fmax(1e-14 * d2, 3.2e-30 * z2)) { conv = true; break; }
                     lim = 1e-2 * dz2;
                 }
-            } else {
-                //@phase track_nonphys_newton
+                ok = ok && conv;
+                z[k] = zk;
+                sum = sum + zk;
+                mag += norm2(zk);
+            }
+        }
+        if (three) {
+            //@phase track_quadratic
+            MLM_COUNT(quadratics);
+            // three DISTINCT images?  (two tracks that collapsed onto one image differ by rounding only)
+            const double tol = 1e-14 * mag;
+            ok = ok && norm2(z[0] - z[1]) > tol && norm2(z[0] - z[2]) > tol && norm2(z[1] - z[2]) > tol;
+            // r4 + r5 = S, r4 r5 = P  ->  z^2 - S z + P = 0 (stable form: the larger root first)
+            const cd ic5 = crcp(c5);
+            const cd S = -(cfma(c4, ic5, sum));
+            const cd P = -(cmul(cmul(c0, ic5), crcp(cmul(cmul(z[0], z[1]), z[2]))));
+            cd sq = csqrt_(rfma(-4.0, P, csq(S)));
+            if (re_mulc(S, sq) < 0.0) sq = -sq;
+            const cd qq = scale(0.5, S + sq);
+            z[3] = qq;
+            z[4] = cmul(P, crcp(qq));
+            //@phase track_nonphys_check
+#pragma unroll
+            for (int k = 3; k < 5; ++k) {
+                MLM_COUNT(nonphys_checks);
+                const cd zs = mk(z[k].x + T.s, z[k].y);
+                const cd W1 = rfma(T.alpha[1], crcp(z[k]), scale(T.beta[1], crcp(zs)));
+                const double f2 = norm2(z[k] - zeta - conj(W1));
+                if (f2 < 1e-2) need_classify = true;  // it may have turned physical (caustic crossing)
+            }
+            //@phase track_polish
+            if (ok && need_classify) {
+                // the candidates are classified like freshly solved roots: bring them to the accuracy of a
+                // polished polynomial root first (the quadratic loses digits where the two roots merge)
+                cd c[6];
+                lens_polynomial(T, zeta, c);
+#pragma unroll
+                for (int k = 3; k < 5; ++k) {
+                    cd zk = z[k];
+                    bool conv = false;
+                    double prev = 1e300;
+#pragma unroll 1
+                    for (int j = 0; j < 6; ++j) {
+                        double dz2;
+                        zk = newton_step(c, zk, dz2);
+                        if (newton_stop(dz2, prev, zk, T.s)) { conv = true; break; }
+                        prev = 0.25 * dz2;
+                    }
+                    ok = ok && conv;
+                    z[k] = zk;
+                }
+            }
+        } else {
+            //@phase track_general
+            cd c[6];
+            lens_polynomial(T, zeta, c);
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                if (k < st.nimg) continue;
                 // non-physical root: Newton on the quintic, then a look at its lens-equation residual
+                cd zk = z[k];
+                bool conv = false;
                 double prev = 1e300;
 #pragma unroll 1
                 for (int j = 0; j < 6; ++j) {
@@ -713,22 +799,23 @@ MLM_HD void advance_images(const LensTable& T, cd zeta, const cd c[6], cd* sz, c
                     if (newton_stop(dz2, prev, zk, T.s)) { conv = true; break; }
                     prev = 0.25 * dz2;
                 }
-                //@phase track_nonphys_check
                 MLM_COUNT(nonphys_checks);
                 const cd zs = mk(zk.x + T.s, zk.y);
                 const cd W1 = rfma(T.alpha[1], crcp(zk), scale(T.beta[1], crcp(zs)));
                 const double f2 = norm2(zk - zeta - conj(W1));
-                if (f2 < 1e-2) need_classify = true;  // it may have turned physical (caustic crossing)
+                if (f2 < 1e-2) need_classify = true;
+                ok = ok && conv;
+                z[k] = zk;
+                sum = sum + zk;
+                mag += norm2(zk);
             }
             //@phase track_vieta
-            ok = ok && conv;
-            z[k] = zk;
-            sum = sum + zk;
-            mag += norm2(zk);
+            // five DISTINCT roots?  (Vieta: sum z_k = -c4/c5; two tracks on one root break it by their separation)
+            const cd v = cfma(c4, crcp(c5), sum);
+            ok = ok && norm2(v) <= 1e-16 * mag;
         }
-        // five DISTINCT roots?  (Vieta: sum z_k = -c4/c5; two tracks on one root break it by their separation)
-        const cd v = cfma(c[4], crcp(c[5]), sum);
-        if (ok && norm2(v) <= 1e-16 * mag) {
+        //@phase track_accept
+        if (ok) {
 #pragma unroll
             for (int k = 0; k < 5; ++k) sz[k * stride] = z[k];
             need_cold = false;
@@ -740,6 +827,8 @@ MLM_HD void advance_images(const LensTable& T, cd zeta, const cd c[6], cd* sz, c
     //@phase cold_glue
     if (need_cold) {
         MLM_COUNT(cold_solves);
+        cd c[6];
+        lens_polynomial(T, zeta, c);
         const int deg = solve_roots(c, T.s, z, flags);
 #pragma unroll
         for (int k = 0; k < 5; ++k) sz[k * stride] = z[k];
@@ -801,13 +890,12 @@ MLM_HD void sum_images(const LensTable& T, const SourceFactors sf, const cd* sz,
 // whole path for one source position (cold start)
 template <int ORDER>
 MLM_HD PointResult point_magnification(const LensTable& T, const SourceFactors sf, cd zeta) {
-    cd c[6], z[5];
+    cd z[5];
     PointResult out;
     out.flags = 0;
     TrackState st;
     st.hist = 0; st.nimg = 0; st.extra = 0;
-    lens_polynomial(T, zeta, c);
-    advance_images(T, zeta, c, z, z, nullptr, 1, st, out.flags);
+    advance_images(T, zeta, z, z, nullptr, 1, st, out.flags);
     sum_images<ORDER>(T, sf, z, 1, st.nimg, out);
     return out;
 }

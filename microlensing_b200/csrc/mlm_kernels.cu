@@ -25,7 +25,7 @@
 // count what a kernel executes): every MLM_COUNT(event) of mlm_core.cuh adds the number of active lanes to
 // g_mlm_cnt[0][event] and 1 to g_mlm_cnt[1][event] (one atomic pair per warp-level event).
 #define MLM_CNT_NAMES(X) X(positions) X(laguerre_evals) X(newton_evals) X(lens_evals) X(track_fallbacks) X(cold_solves) \
-    X(classify_calls) X(classify_newton) X(nonphys_checks) X(images)
+    X(classify_calls) X(classify_newton) X(nonphys_checks) X(images) X(quadratics)
 enum {
 #define X(n) MLM_CNT_##n,
     MLM_CNT_NAMES(X)
@@ -105,12 +105,10 @@ k_points(const __grid_constant__ LensTable T, const SourceFactors sf, const doub
             ratio = re_mulc(d, dprev) * rcp(norm2(dprev));
             if (!(ratio > 0.0 && ratio < 4.0)) st.hist = 1;
         }
-        cd c[6];
         PointResult r;
         r.flags = 0;
         MLM_COUNT(positions);
-        lens_polynomial(T, zt, c);
-        advance_images(T, zt, c, sz, szp, nullptr, MLM_BLOCK, st, r.flags, ratio);
+        advance_images(T, zt, sz, szp, nullptr, MLM_BLOCK, st, r.flags, ratio);
         sum_images<ORDER>(T, sf, sz, MLM_BLOCK, st.nimg, r);
         store_result(r, i, A0, A2, A4, nimg, flags);
         zprev = zt;
@@ -165,12 +163,10 @@ k_map(const __grid_constant__ LensTable T, const SourceFactors sf, double x0, do
         for (int64_t r = ra; r < rb; ++r) {
             const double y = __dadd_rn(y0, __dmul_rn((double)r + 0.5, dy));
             const cd zeta = mk(x, y);
-            cd c[6];
             PointResult res;
             res.flags = 0;
             MLM_COUNT(positions);
-            lens_polynomial(T, zeta, c);
-            advance_images(T, zeta, c, sz, szp, szpp, MLM_BLOCK, st, res.flags);
+            advance_images(T, zeta, sz, szp, szpp, MLM_BLOCK, st, res.flags);
             sum_images<ORDER>(T, sf, sz, MLM_BLOCK, st.nimg, res);
             store_result(res, (r - row0) * nx + col, A0, A2, A4, nimg, flags);
         }
@@ -262,12 +258,10 @@ k_models(const double* __restrict__ s, const double* __restrict__ q, const doubl
                 const double zx = __dadd_rn(__dadd_rn(__dmul_rn(tau, rot[0]), -ur1), -rot[2]);
                 const double zy = __dadd_rn(__dmul_rn(tau, rot[1]), ur0);
                 const cd zeta = mk(zx, zy);
-                cd c[6];
                 PointResult res;
                 res.flags = 0;
                 MLM_COUNT(positions);
-                lens_polynomial(T, zeta, c);
-                advance_images(T, zeta, c, sz, szp, szpp, MLM_MODELS_BLOCK, st, res.flags, ratio);
+                advance_images(T, zeta, sz, szp, szpp, MLM_MODELS_BLOCK, st, res.flags, ratio);
                 sum_images<ORDER>(T, sf, sz, MLM_MODELS_BLOCK, st.nimg, res);
                 store_result(res, m * Tn + t, A0, A2, A4, nimg, flags);
             }
@@ -324,12 +318,10 @@ k_models_chi2(const double* __restrict__ s, const double* __restrict__ q, const 
                 const double zx = __dadd_rn(__dadd_rn(__dmul_rn(tau, rot[0]), -ur1), -rot[2]);
                 const double zy = __dadd_rn(__dmul_rn(tau, rot[1]), ur0);
                 const cd zeta = mk(zx, zy);
-                cd c[6];
                 PointResult res;
                 res.flags = 0;
                 MLM_COUNT(positions);
-                lens_polynomial(T, zeta, c);
-                advance_images(T, zeta, c, sz, szp, szpp, MLM_MODELS_BLOCK, st, res.flags, ratio);
+                advance_images(T, zeta, sz, szp, szpp, MLM_MODELS_BLOCK, st, res.flags, ratio);
                 sum_images<ORDER>(T, sf, sz, MLM_MODELS_BLOCK, st.nimg, res);
                 const double A = (ORDER >= 4) ? res.A4 : res.A2;
                 const double w = __ldg(weight + t), f = __ldg(flux + t);

@@ -3,7 +3,7 @@
 // recursion) against the oracle without a GPU.  Never loaded by microlensing_b200.
 #ifdef MLM_STATS
 static long g_cnt_laguerre_evals = 0, g_cnt_newton_evals = 0, g_cnt_track_fallbacks = 0, g_cnt_lens_evals = 0;
-static long g_cnt_cold_solves = 0, g_cnt_classify_calls = 0, g_cnt_classify_newton = 0, g_cnt_nonphys_checks = 0, g_cnt_images = 0;
+static long g_cnt_cold_solves = 0, g_cnt_classify_calls = 0, g_cnt_classify_newton = 0, g_cnt_nonphys_checks = 0, g_cnt_images = 0, g_cnt_quadratics = 0;
 #define MLM_COUNT(name) (++g_cnt_##name)
 #endif
 #include "../../microlensing_b200/csrc/mlm_core.cuh"
@@ -81,12 +81,10 @@ extern "C" void emu_strip(double s, double q, double rho, double Gamma, const do
     for (long i = 0; i < n; ++i) {
         if (i % strip == 0) st.hist = 0;
         cd zeta_i = mk(zeta[2 * i], zeta[2 * i + 1]);
-        cd c[6];
         PointResult r;
         r.flags = 0;
-        lens_polynomial(T, zeta_i, c);
         const int before = st.hist;
-        advance_images(T, zeta_i, c, z, zp, g_quadratic ? zpp : nullptr, 1, st, r.flags);
+        advance_images(T, zeta_i, z, zp, g_quadratic ? zpp : nullptr, 1, st, r.flags);
         if (before == 0 || st.hist < 2) ++cold;
         sum_images<4>(T, sf, z, 1, st.nimg, r);
         A0[i] = r.A0; A2[i] = r.A2; A4[i] = r.A4;

@@ -36,7 +36,7 @@ def run(M=200, T=2000, L=32, seed=1, qlo=1e-4, quadratic=1, slo=0.5, shi=2.0, u0
                 i = np.where(ok & (rel > 1e-9))[0]
                 print('model', m, 'rel', w, 'at', i[:5], 'q', q[m])
             worst = max(worst, w)
-        cold += nc; tot += T; nflag += ((fl & 3) != 0).sum()
+        cold += nc; tot += T; nflag += ((fl & 1) != 0).sum()
     print(f'M={M} T={T} L={L}: nimg mismatches {nbad}, max rel (unflagged) {worst:.2e}, cold fraction {cold / tot:.4f}, noconv flags {nflag}')
     return nbad, worst
 
