@@ -673,141 +673,128 @@ struct TrackState {
 // re-classified.  Only c0, c4, c5 of the polynomial are needed for that; the full polynomial is formed on the rare
 // paths (polish, cold solve) and in the other states (five images: Vieta check of the five tracks; 1, 2 or 4
 // images -- degenerate positions: non-physical roots carried by Newton on the quintic).
+// start value of root k from its history (mode 0: the previous root, 1: linear extrapolation scaled by `ratio`,
+// 2: linear 2 z1 - z2, 3: quadratic 3 z1 - 3 z2 + z3), shifting the history of that root by one position
+MLM_HD cd predict_root(cd* sz, cd* szp, cd* szpp, int mode, double ratio) {
+    const cd zc = *sz;
+    cd pred = zc;
+    if (mode) {
+        const cd zo = *szp;
+        if (mode == 3) {
+            const cd zoo = *szpp;
+            pred = mk(fma(3.0, zc.x - zo.x, zoo.x), fma(3.0, zc.y - zo.y, zoo.y));
+        } else if (mode == 2) {
+            pred = mk(fma(2.0, zc.x, -zo.x), fma(2.0, zc.y, -zo.y));
+        } else {
+            pred = mk(fma(ratio, zc.x - zo.x, zc.x), fma(ratio, zc.y - zo.y, zc.y));
+        }
+        if (szpp != nullptr) *szpp = zo;
+    }
+    *szp = zc;
+    return pred;
+}
+
+// |z - zeta - conj(W1(z))|^2: the quantity the reference compares with 1e-6 (multipoles.py:182-183)
+MLM_HD double lens_residual2(const LensTable& T, cd zeta, cd z) {
+    const cd zs = mk(z.x + T.s, z.y);
+    const cd W1 = rfma(T.alpha[1], crcp(z), scale(T.beta[1], crcp(zs)));
+    return norm2(z - zeta - conj(W1));
+}
+
+// Newton on the quintic from zk until newton_stop (at most 6 steps); false: not converged
+MLM_HD bool quintic_newton(const cd c[6], double s, cd& zk) {
+    double prev = 1e300;
+#pragma unroll 1
+    for (int j = 0; j < 6; ++j) {
+        double dz2;
+        zk = newton_step(c, zk, dz2);
+        if (newton_stop(dz2, prev, zk, s)) return true;
+        prev = 0.25 * dz2;
+    }
+    return false;
+}
+
 MLM_HD void advance_images(const LensTable& T, cd zeta, cd* sz, cd* szp, cd* szpp, int stride,
                            TrackState& st, unsigned& flags, double ratio = 1.0) {
     bool need_cold = true, need_classify = false;
-    cd z[5];
     cd c0, c4, c5;
     lens_polynomial_c045(T, zeta, c0, c4, c5);
-    //@phase track_extrapolate            (markers: regions of the per-phase instruction table, tools/ncu_phase_table.py)
     if (st.hist >= 1 && !(c5.x == 0.0 && c5.y == 0.0)) {
-        const bool three = (st.nimg == 3);
-        const int ncarried = three ? 3 : 5;           // roots that are iterated from their predecessors
-        // start values: previous roots, linear (2 z1 - z2) or quadratic (3 z1 - 3 z2 + z3) extrapolation
-#pragma unroll
-        for (int k = 0; k < 5; ++k) {
-            if (k < ncarried) {
-                const cd zc = sz[k * stride];
-                cd pred = zc;
-                if (st.hist >= 2) {
-                    const cd zo = szp[k * stride];
-                    if (ratio == 1.0) {
-                        if (szpp != nullptr && st.hist >= 3) {
-                            const cd zoo = szpp[k * stride];
-                            pred = mk(fma(3.0, zc.x - zo.x, zoo.x), fma(3.0, zc.y - zo.y, zoo.y));
-                        } else {
-                            pred = mk(fma(2.0, zc.x, -zo.x), fma(2.0, zc.y, -zo.y));
-                        }
-                    } else {
-                        pred = mk(fma(ratio, zc.x - zo.x, zc.x), fma(ratio, zc.y - zo.y, zc.y));
-                    }
-                    if (szpp != nullptr) szpp[k * stride] = zo;
-                }
-                szp[k * stride] = zc;
-                z[k] = pred;
-            }
-        }
-        //@phase track_image_newton
+        //@phase track_image_newton       (markers: regions of the per-phase instruction table, tools/ncu_phase_table.py)
+        const int nimg = st.nimg;
+        const int mode = (st.hist < 2) ? 0 : ((ratio != 1.0) ? 1 : ((szpp != nullptr && st.hist >= 3) ? 3 : 2));
         bool ok = true;
         cd sum = mk(0.0, 0.0);
         double mag = 1.0;
-#pragma unroll
-        for (int k = 0; k < 5; ++k) {
-            if (k < st.nimg) {
-                // physical image: Newton on the lens equation.  A step below 1e-7 d leaves an error of
-                // ~ (1e-7 d)^2 / d = 1e-14 d: done; every further step must contract by >= 10.
-                cd zk = z[k];
-                bool conv = false;
-                double lim = 1e300;
+        // the images: Newton on the lens equation from the extrapolated position.  A step below 1e-7 d leaves an
+        // error of ~ (1e-7 d)^2 / d = 1e-14 d: done; every further step must contract by >= 10.  The results go
+        // straight into the store: a rejected position is solved cold, which rewrites all of it.
 #pragma unroll 1
-                for (int it = 0; it < 4; ++it) {
-                    double dz2, d2, z2;
-                    const cd zn = lens_newton(T, zeta, zk, dz2, d2, z2);
-                    MLM_COUNT(lens_evals);
-                    if (!(dz2 < lim)) break;
-                    zk = zn;
-                    if (dz2 <= fmax(1e-14 * d2, 3.2e-30 * z2)) { conv = true; break; }
-                    lim = 1e-2 * dz2;
-                }
-                ok = ok && conv;
-                z[k] = zk;
-                sum = sum + zk;
-                mag += norm2(zk);
+        for (int k = 0; k < nimg; ++k) {
+            cd zk = predict_root(sz + k * stride, szp + k * stride, szpp ? szpp + k * stride : nullptr, mode, ratio);
+            bool conv = false;
+            double lim = 1e300;
+#pragma unroll 1
+            for (int it = 0; it < 4; ++it) {
+                double dz2, d2, z2;
+                const cd zn = lens_newton(T, zeta, zk, dz2, d2, z2);
+                MLM_COUNT(lens_evals);
+                if (!(dz2 < lim)) break;
+                zk = zn;
+                if (dz2 <= fmax(1e-14 * d2, 3.2e-30 * z2)) { conv = true; break; }
+                lim = 1e-2 * dz2;
             }
+            ok = ok && conv;
+            sz[k * stride] = zk;
+            sum = sum + zk;
+            mag += norm2(zk);
         }
-        if (three) {
+        if (nimg == 3) {
             //@phase track_quadratic
             MLM_COUNT(quadratics);
+            const cd z0 = sz[0], z1 = sz[stride], z2 = sz[2 * stride];
             // three DISTINCT images?  (two tracks that collapsed onto one image differ by rounding only)
             const double tol = 1e-14 * mag;
-            ok = ok && norm2(z[0] - z[1]) > tol && norm2(z[0] - z[2]) > tol && norm2(z[1] - z[2]) > tol;
+            ok = ok && norm2(z0 - z1) > tol && norm2(z0 - z2) > tol && norm2(z1 - z2) > tol;
             // r4 + r5 = S, r4 r5 = P  ->  z^2 - S z + P = 0 (stable form: the larger root first)
             const cd ic5 = crcp(c5);
             const cd S = -(cfma(c4, ic5, sum));
-            const cd P = -(cmul(cmul(c0, ic5), crcp(cmul(cmul(z[0], z[1]), z[2]))));
+            const cd P = -(cmul(cmul(c0, ic5), crcp(cmul(cmul(z0, z1), z2))));
             cd sq = csqrt_(rfma(-4.0, P, csq(S)));
             if (re_mulc(S, sq) < 0.0) sq = -sq;
-            const cd qq = scale(0.5, S + sq);
-            z[3] = qq;
-            z[4] = cmul(P, crcp(qq));
+            cd r4 = scale(0.5, S + sq);
+            cd r5 = cmul(P, crcp(r4));
             //@phase track_nonphys_check
-#pragma unroll
-            for (int k = 3; k < 5; ++k) {
-                MLM_COUNT(nonphys_checks);
-                const cd zs = mk(z[k].x + T.s, z[k].y);
-                const cd W1 = rfma(T.alpha[1], crcp(z[k]), scale(T.beta[1], crcp(zs)));
-                const double f2 = norm2(z[k] - zeta - conj(W1));
-                if (f2 < 1e-2) need_classify = true;  // it may have turned physical (caustic crossing)
-            }
-            //@phase track_polish
-            if (ok && need_classify) {
-                // the candidates are classified like freshly solved roots: bring them to the accuracy of a
-                // polished polynomial root first (the quadratic loses digits where the two roots merge)
+            MLM_COUNT(nonphys_checks);
+            MLM_COUNT(nonphys_checks);
+            if (lens_residual2(T, zeta, r4) < 1e-2 || lens_residual2(T, zeta, r5) < 1e-2) {
+                //@phase track_polish
+                // they may have turned physical (caustic crossing): classify them like freshly solved roots, i.e.
+                // at the accuracy of a polished polynomial root (the quadratic loses digits where the two merge)
+                need_classify = true;
                 cd c[6];
                 lens_polynomial(T, zeta, c);
-#pragma unroll
-                for (int k = 3; k < 5; ++k) {
-                    cd zk = z[k];
-                    bool conv = false;
-                    double prev = 1e300;
-#pragma unroll 1
-                    for (int j = 0; j < 6; ++j) {
-                        double dz2;
-                        zk = newton_step(c, zk, dz2);
-                        if (newton_stop(dz2, prev, zk, T.s)) { conv = true; break; }
-                        prev = 0.25 * dz2;
-                    }
-                    ok = ok && conv;
-                    z[k] = zk;
-                }
+                ok = quintic_newton(c, T.s, r4) && ok;
+                ok = quintic_newton(c, T.s, r5) && ok;
             }
+            sz[3 * stride] = r4;
+            sz[4 * stride] = r5;
         } else {
             //@phase track_general
-            cd c[6];
-            lens_polynomial(T, zeta, c);
-#pragma unroll
-            for (int k = 0; k < 5; ++k) {
-                if (k < st.nimg) continue;
-                // non-physical root: Newton on the quintic, then a look at its lens-equation residual
-                cd zk = z[k];
-                bool conv = false;
-                double prev = 1e300;
+            if (nimg < 5) {
+                cd c[6];
+                lens_polynomial(T, zeta, c);
 #pragma unroll 1
-                for (int j = 0; j < 6; ++j) {
-                    double dz2;
-                    zk = newton_step(c, zk, dz2);
-                    if (newton_stop(dz2, prev, zk, T.s)) { conv = true; break; }
-                    prev = 0.25 * dz2;
+                for (int k = nimg; k < 5; ++k) {
+                    // non-physical root: Newton on the quintic, then a look at its lens-equation residual
+                    cd zk = predict_root(sz + k * stride, szp + k * stride, szpp ? szpp + k * stride : nullptr, mode, ratio);
+                    ok = quintic_newton(c, T.s, zk) && ok;
+                    MLM_COUNT(nonphys_checks);
+                    if (lens_residual2(T, zeta, zk) < 1e-2) need_classify = true;
+                    sz[k * stride] = zk;
+                    sum = sum + zk;
+                    mag += norm2(zk);
                 }
-                MLM_COUNT(nonphys_checks);
-                const cd zs = mk(zk.x + T.s, zk.y);
-                const cd W1 = rfma(T.alpha[1], crcp(zk), scale(T.beta[1], crcp(zs)));
-                const double f2 = norm2(zk - zeta - conj(W1));
-                if (f2 < 1e-2) need_classify = true;
-                ok = ok && conv;
-                z[k] = zk;
-                sum = sum + zk;
-                mag += norm2(zk);
             }
             //@phase track_vieta
             // five DISTINCT roots?  (Vieta: sum z_k = -c4/c5; two tracks on one root break it by their separation)
@@ -816,8 +803,6 @@ MLM_HD void advance_images(const LensTable& T, cd zeta, cd* sz, cd* szp, cd* szp
         }
         //@phase track_accept
         if (ok) {
-#pragma unroll
-            for (int k = 0; k < 5; ++k) sz[k * stride] = z[k];
             need_cold = false;
             st.hist = (szpp != nullptr && st.hist >= 2) ? 3 : 2;
         } else {
@@ -827,7 +812,7 @@ MLM_HD void advance_images(const LensTable& T, cd zeta, cd* sz, cd* szp, cd* szp
     //@phase cold_glue
     if (need_cold) {
         MLM_COUNT(cold_solves);
-        cd c[6];
+        cd c[6], z[5];
         lens_polynomial(T, zeta, c);
         const int deg = solve_roots(c, T.s, z, flags);
 #pragma unroll
