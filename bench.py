@@ -756,7 +756,7 @@ def time_models_sharded(par, T, rank, world, dev, steps, warmup, barrier, fit=No
     t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    res = {"ms": float(t[0]), "launches_per_step": (ctx.launch_count() - l0) // steps}
+    res = {"ms": float(t[0]), "launches_per_step": (ctx.launch_count() - l0) // steps, "segment": sm.segment}
     extra = {}
     if rank == 0:
         M = len(par[0])
@@ -767,7 +767,7 @@ def time_models_sharded(par, T, rank, world, dev, steps, warmup, barrier, fit=No
         if fit is None:
             b = [torch.empty(len(pick) * T, dtype=torch.float64, device=dev) for _ in range(3)] + \
                 [torch.empty(len(pick) * T, dtype=torch.uint8, device=dev) for _ in range(2)]
-            models_device(*p1, len(pick), -2.0, 4.0 / T, T, *b, stream=st, device=dev.index)
+            models_device(*p1, len(pick), -2.0, 4.0 / T, T, *b, stream=st, device=dev.index, segment=sm.segment)
             torch.cuda.synchronize()
             for key, t_ in zip(("A0", "A2", "A4", "nimg", "flags"), b):
                 if key in sm.outputs:
@@ -777,7 +777,8 @@ def time_models_sharded(par, T, rank, world, dev, steps, warmup, barrier, fit=No
             extra["flux_of_model_0"] = (2.0 * sm.full["A4"][0].cpu().numpy() + 0.5) if "A4" in sm.outputs else None
         else:
             stats = torch.empty(len(pick) * 8, dtype=torch.float64, device=dev)
-            models_chi2_device(*p1, len(pick), -2.0, 4.0 / T, T, sm.fit[0], sm.fit[1], stats, stream=st, device=dev.index)
+            models_chi2_device(*p1, len(pick), -2.0, 4.0 / T, T, sm.fit[0], sm.fit[1], stats, stream=st, device=dev.index,
+                               segment=sm.segment)
             torch.cuda.synchronize()
             got = sm.full["stats"][torch.as_tensor(pick, device=dev)].reshape(-1).view(torch.uint8)
             bad += int((got != stats.view(torch.uint8)).sum())
@@ -809,7 +810,8 @@ def other_configs(mb, dev, rank, world, barrier, reps=3):
     r2, ex2 = time_models_sharded(par, T, rank, world, dev, reps, 2, barrier, fit=(flux, np.full(T, 0.01)))
     if rank == 0:
         out["C5_models_1e4x2000"] = dict(positions=n, ms=r1["ms"], mags_per_s=n / (r1["ms"] * 1e-3), f5=ex1.get("f5"),
-                                         kernel="k_models<4>", sharded_vs_single=r1.get("sharded_vs_single"),
+                                         kernel="k_models<4>", segment_epochs=r1.get("segment"),
+                                         sharded_vs_single=r1.get("sharded_vs_single"),
                                          gather="26 B/epoch to rank 0 (bulk peer copies of contiguous model blocks)" if world > 1 else "none",
                                          n_gpus=world)
         out["C5_models_1e4x2000_chi2"] = dict(positions=n, ms=r2["ms"], mags_per_s=n / (r2["ms"] * 1e-3),

@@ -115,6 +115,14 @@ int mlm_auto_strip(mlm_context* ctx, int64_t nx, int64_t nrows);
 int mlm_points(mlm_context* ctx, double s, double q, double rho, double Gamma,
                const double* zeta, int64_t n, int order,
                double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags, void* stream);
+/* The same for a list WITHOUT spatial order (random positions, a shuffled catalogue): the entries are visited along
+ * a space-filling curve (Morton keys on a 65536^2 grid over their bounding box, radix-sorted on the device), so that
+ * consecutive visits are neighbours in the source plane and the images can be carried from one to the next instead of
+ * a cold solve per entry; results land at the entries' own indices.  n < 2^32.  Worth it when fewer than about half of
+ * the consecutive entries are within 0.02 Einstein radii of each other (mlm_points_host checks a sample and picks). */
+int mlm_points_unordered(mlm_context* ctx, double s, double q, double rho, double Gamma,
+                         const double* zeta, int64_t n, int order,
+                         double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags, void* stream);
 int mlm_points_host(mlm_context* ctx, double s, double q, double rho, double Gamma,
                     const double* zeta, int64_t n, int order,
                     double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags);
@@ -153,14 +161,18 @@ int mlm_map_host(mlm_context* ctx, double s, double q, double rho, double Gamma,
 
 /* Batched model grid: M models x T epochs.  Model m has (s,q,rho,Gamma,u0,alpha)[m] (device
  * arrays of length M); epoch t has tau = tau0 + t dtau; centre-of-mass source position
- * zeta_cm = (tau + i u0) exp(i alpha).  Outputs are [m * T + t].  One block per model; the threads walk
- * segments of <= 32 consecutive epochs (a function of T only: a model's light curve does not depend on
- * how the grid is sharded over GPUs). */
+ * zeta_cm = (tau + i u0) exp(i alpha).  Outputs are [m * T + t].  A thread walks a SEGMENT of `seg` consecutive
+ * epochs of one model with warm-started root tracking (cold solve at the segment start); blocks of 64 threads serve
+ * 1..16 models at a time.  `seg` is a numerical parameter like the strip length of a map: the bits of a light curve
+ * depend on it (results for different seg agree to rounding), NOT on M or on how the grid is sharded over GPUs --
+ * shards of one grid must be computed with ONE seg.  seg = 0 chooses mlm_auto_segment(M, T) of THIS call (long
+ * segments as long as the grid fills the GPU: 128 epochs for 1e4 x 2000, 9 for 1 x 1e6; env MLM_SEGMENT overrides). */
+int mlm_auto_segment(mlm_context* ctx, int64_t M, int64_t T);
 int mlm_models(mlm_context* ctx, const double* s, const double* q, const double* rho, const double* Gamma,
-               const double* u0, const double* alpha, int64_t M, double tau0, double dtau, int64_t T, int order,
+               const double* u0, const double* alpha, int64_t M, double tau0, double dtau, int64_t T, int order, int seg,
                double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags, void* stream);
 int mlm_models_host(mlm_context* ctx, const double* s, const double* q, const double* rho, const double* Gamma,
-                    const double* u0, const double* alpha, int64_t M, double tau0, double dtau, int64_t T, int order,
+                    const double* u0, const double* alpha, int64_t M, double tau0, double dtau, int64_t T, int order, int seg,
                     double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags);
 
 /* The same with OBSERVATION TIMES instead of a uniform grid ("in-kernel trajectory
@@ -170,11 +182,11 @@ int mlm_models_host(mlm_context* ctx, const double* s, const double* q, const do
  * more than 0.02 Einstein times restarts cold. */
 int mlm_models_times(mlm_context* ctx, const double* s, const double* q, const double* rho, const double* Gamma,
                      const double* u0, const double* alpha, const double* t0, const double* tE, int64_t M,
-                     const double* times, int64_t T, int order,
+                     const double* times, int64_t T, int order, int seg,
                      double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags, void* stream);
 int mlm_models_times_host(mlm_context* ctx, const double* s, const double* q, const double* rho, const double* Gamma,
                           const double* u0, const double* alpha, const double* t0, const double* tE, int64_t M,
-                          const double* times, int64_t T, int order,
+                          const double* times, int64_t T, int order, int seg,
                           double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags);
 
 /* Model grid with the light-curve fit fused in ("fused chi^2 reduction against observed
@@ -182,22 +194,22 @@ int mlm_models_times_host(mlm_context* ctx, const double* s, const double* q, co
  * per model, the least-squares linear flux fit F_t = Fs A_t + Fb of the model magnifications A_t (A4 for
  * order 4, A2 for order 2) to the observed fluxes flux[T] with weights weight[T] = 1/sigma^2:
  *   stats[8 m + 0..7] = { chi2_min, Fs, Fb, sum w A, sum w A^2, sum w A f, #epochs with 5 images, #flagged epochs }
- * (per-block fixed-order reduction: deterministic). */
+ * (fixed-order reduction over the threads of a model: deterministic; seg as in mlm_models). */
 int mlm_models_chi2(mlm_context* ctx, const double* s, const double* q, const double* rho, const double* Gamma,
-                    const double* u0, const double* alpha, int64_t M, double tau0, double dtau, int64_t T, int order,
+                    const double* u0, const double* alpha, int64_t M, double tau0, double dtau, int64_t T, int order, int seg,
                     const double* flux, const double* weight, double* stats, void* stream);
 int mlm_models_chi2_host(mlm_context* ctx, const double* s, const double* q, const double* rho, const double* Gamma,
-                         const double* u0, const double* alpha, int64_t M, double tau0, double dtau, int64_t T, int order,
+                         const double* u0, const double* alpha, int64_t M, double tau0, double dtau, int64_t T, int order, int seg,
                          const double* flux, const double* weight, double* stats);
 
 /* ... and against a light curve observed at times[T] (t0, tE per model as in mlm_models_times). */
 int mlm_models_chi2_times(mlm_context* ctx, const double* s, const double* q, const double* rho, const double* Gamma,
                           const double* u0, const double* alpha, const double* t0, const double* tE, int64_t M,
-                          const double* times, int64_t T, int order,
+                          const double* times, int64_t T, int order, int seg,
                           const double* flux, const double* weight, double* stats, void* stream);
 int mlm_models_chi2_times_host(mlm_context* ctx, const double* s, const double* q, const double* rho, const double* Gamma,
                                const double* u0, const double* alpha, const double* t0, const double* tE, int64_t M,
-                               const double* times, int64_t T, int order,
+                               const double* times, int64_t T, int order, int seg,
                                const double* flux, const double* weight, double* stats);
 
 /* ---- drop-ins for the individual reference functions ------------------------------------ */

@@ -40,20 +40,22 @@ SIGNATURES = {
     "mlm_ipc_close": [_P, _P],
     "mlm_memcpy_async": [_P, _P, _P, _L, _P],
     "mlm_points": [_P, _D, _D, _D, _D, _P, _L, _I, _P, _P, _P, _P, _P, _P],
+    "mlm_points_unordered": [_P, _D, _D, _D, _D, _P, _L, _I, _P, _P, _P, _P, _P, _P],
     "mlm_points_host": [_P, _D, _D, _D, _D, _P, _L, _I, _P, _P, _P, _P, _P],
     "mlm_map": [_P, _D, _D, _D, _D, _D, _D, _D, _D, _L, _L, _L, _I, _I, _P, _P, _P, _P, _P, _P],
     "mlm_map_deal": [_P, _D, _D, _D, _D, _D, _D, _D, _D, _L, _L, _L, _L, _I, ctypes.POINTER(ctypes.c_int32), _I, _I,
                      _P, _P, _P, _P, _P, _P],
     "mlm_map_strips": [_P, _D, _D, _D, _D, _D, _D, _D, _D, _L, _L, _L, _L, _L, _I, _I, _P, _P, _P, _P, _P, _P],
     "mlm_map_host": [_P, _D, _D, _D, _D, _D, _D, _D, _D, _L, _L, _L, _I, _I, _P, _P, _P, _P, _P],
-    "mlm_models": [_P, _P, _P, _P, _P, _P, _P, _L, _D, _D, _L, _I, _P, _P, _P, _P, _P, _P],
-    "mlm_models_host": [_P, _P, _P, _P, _P, _P, _P, _L, _D, _D, _L, _I, _P, _P, _P, _P, _P],
-    "mlm_models_times": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P, _L, _I, _P, _P, _P, _P, _P, _P],
-    "mlm_models_times_host": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P, _L, _I, _P, _P, _P, _P, _P],
-    "mlm_models_chi2_times": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P, _L, _I, _P, _P, _P, _P],
-    "mlm_models_chi2_times_host": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P, _L, _I, _P, _P, _P],
-    "mlm_models_chi2": [_P, _P, _P, _P, _P, _P, _P, _L, _D, _D, _L, _I, _P, _P, _P, _P],
-    "mlm_models_chi2_host": [_P, _P, _P, _P, _P, _P, _P, _L, _D, _D, _L, _I, _P, _P, _P],
+    "mlm_auto_segment": [_P, _L, _L],
+    "mlm_models": [_P, _P, _P, _P, _P, _P, _P, _L, _D, _D, _L, _I, _I, _P, _P, _P, _P, _P, _P],
+    "mlm_models_host": [_P, _P, _P, _P, _P, _P, _P, _L, _D, _D, _L, _I, _I, _P, _P, _P, _P, _P],
+    "mlm_models_times": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P, _L, _I, _I, _P, _P, _P, _P, _P, _P],
+    "mlm_models_times_host": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P, _L, _I, _I, _P, _P, _P, _P, _P],
+    "mlm_models_chi2_times": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P, _L, _I, _I, _P, _P, _P, _P],
+    "mlm_models_chi2_times_host": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P, _L, _I, _I, _P, _P, _P],
+    "mlm_models_chi2": [_P, _P, _P, _P, _P, _P, _P, _L, _D, _D, _L, _I, _I, _P, _P, _P, _P],
+    "mlm_models_chi2_host": [_P, _P, _P, _P, _P, _P, _P, _L, _D, _D, _L, _I, _I, _P, _P, _P],
     "mlm_from_wk": [_P, _P, _L, _I, _D, _D, _P, _P],
     "mlm_from_wk_host": [_P, _P, _L, _I, _D, _D, _P],
     "mlm_solve": [_P, _D, _D, _P, _L, _P, _P],
@@ -139,6 +141,13 @@ class Context:
         v = int(self.lib.mlm_auto_strip(self.handle, int(nx), int(nrows)))
         if v <= 0:
             raise ValueError("mlm_auto_strip: bad argument")
+        return v
+
+    def auto_segment(self, M: int, T: int) -> int:
+        """Epochs per tracking segment the model-grid entry points choose for seg=0 on a grid of M x T."""
+        v = int(self.lib.mlm_auto_segment(self.handle, int(M), int(T)))
+        if v <= 0:
+            raise ValueError("mlm_auto_segment: bad argument")
         return v
 
     def host_register(self, address: int, nbytes: int):

@@ -140,10 +140,13 @@ def _model_arrays(what, s, q, rho, Gamma, u0, alpha, t0=None, tE=None):
 
 
 def magnification_models(s, q, rho, Gamma, u0, alpha, tau0=None, dtau=None, T=None, order=4, out=None, device=None,
-                         outputs=ALL_OUTPUTS, times=None, t0=None, tE=None) -> Magnification:
+                         outputs=ALL_OUTPUTS, times=None, t0=None, tE=None, segment=0) -> Magnification:
     """Batched fit grid: M models (arrays s, q, rho, Gamma, u0, alpha of length M) x T epochs, either on the
     uniform grid tau = tau0 + t dtau, or at observation `times` (any spacing) with per-model (or scalar) time of
-    closest approach t0 and Einstein time tE: tau = (times - t0) / tE."""
+    closest approach t0 and Einstein time tE: tau = (times - t0) / tE.
+    `segment` = epochs a thread tracks before it starts afresh (numerical parameter, see mlm_models in
+    include/mlmultipoles.h; 0: chosen from M and T of this call -- parts of ONE grid computed by separate calls
+    are bit-identical to the grid computed at once only if they pass the same segment)."""
     ctx = _capi.context(device)
     if times is None:
         if tau0 is None or dtau is None or T is None:
@@ -160,16 +163,16 @@ def magnification_models(s, q, rho, Gamma, u0, alpha, tau0=None, dtau=None, T=No
         out = alloc_outputs(shape, device, pinned=M * T >= (1 << 16), outputs=outputs)
     _check_out(out, shape)
     if times is None:
-        ctx.check(ctx.lib.mlm_models_host(ctx.handle, *[_capi.ptr(a) for a in arrs], M, tau0, dtau, T, order,
+        ctx.check(ctx.lib.mlm_models_host(ctx.handle, *[_capi.ptr(a) for a in arrs], M, tau0, dtau, T, order, int(segment),
                                           *_out_ptrs(out)), "mlm_models_host")
     else:
         ctx.check(ctx.lib.mlm_models_times_host(ctx.handle, *[_capi.ptr(a) for a in arrs], M, _capi.ptr(times), T, order,
-                                                *_out_ptrs(out)), "mlm_models_times_host")
+                                                int(segment), *_out_ptrs(out)), "mlm_models_times_host")
     return out
 
 
 def models_chi2(s, q, rho, Gamma, u0, alpha, tau0=None, dtau=None, flux=None, sigma=None, order=4, device=None,
-                times=None, t0=None, tE=None) -> dict:
+                times=None, t0=None, tE=None, segment=0) -> dict:
     """Fit statistics of a grid of M models against ONE observed light curve: the model
     magnifications never leave the GPU.  `flux`, `sigma`: observed fluxes and their errors at the epochs
     tau_t = tau0 + t dtau, or at the observation `times` with per-model (or scalar) t0, tE:
@@ -197,10 +200,12 @@ def models_chi2(s, q, rho, Gamma, u0, alpha, tau0=None, dtau=None, flux=None, si
     stats = np.empty((M, 8), dtype=np.float64)
     if times is None:
         ctx.check(ctx.lib.mlm_models_chi2_host(ctx.handle, *[_capi.ptr(a) for a in arrs], M, tau0, dtau, flux.size, order,
-                                               _capi.ptr(flux), _capi.ptr(w), _capi.ptr(stats)), "mlm_models_chi2_host")
+                                               int(segment), _capi.ptr(flux), _capi.ptr(w), _capi.ptr(stats)),
+                  "mlm_models_chi2_host")
     else:
         ctx.check(ctx.lib.mlm_models_chi2_times_host(ctx.handle, *[_capi.ptr(a) for a in arrs], M, _capi.ptr(times),
-                                                     flux.size, order, _capi.ptr(flux), _capi.ptr(w), _capi.ptr(stats)),
+                                                     flux.size, order, int(segment), _capi.ptr(flux), _capi.ptr(w),
+                                                     _capi.ptr(stats)),
                   "mlm_models_chi2_times_host")
     keys = ("chi2", "Fs", "Fb", "SA", "SAA", "SAF", "n5", "nflag")
     return Magnification({k: stats[:, i].copy() for i, k in enumerate(keys)})
@@ -211,10 +216,14 @@ def _p(x):
     return _capi.ptr(x)
 
 
-def points_device(s, q, rho, Gamma, zeta, n, A0, A2, A4, nimg=None, flags=None, order=4, stream=None, device=None):
+def points_device(s, q, rho, Gamma, zeta, n, A0, A2, A4, nimg=None, flags=None, order=4, stream=None, device=None,
+                  unordered=False):
+    """unordered=True: the list has no spatial order -- visit it along a space-filling curve (mlm_points_unordered:
+    device radix sort of Morton keys) so that the images can be carried between neighbours."""
     ctx = _capi.context(device)
-    ctx.check(ctx.lib.mlm_points(ctx.handle, s, q, rho, Gamma, _p(zeta), n, order, _p(A0), _p(A2), _p(A4),
-                                 _p(nimg), _p(flags), _p(stream)), "mlm_points")
+    fn, name = (ctx.lib.mlm_points_unordered, "mlm_points_unordered") if unordered else (ctx.lib.mlm_points, "mlm_points")
+    ctx.check(fn(ctx.handle, s, q, rho, Gamma, _p(zeta), n, order, _p(A0), _p(A2), _p(A4), _p(nimg), _p(flags), _p(stream)),
+              name)
 
 
 def map_device(s, q, rho, Gamma, x0, y0, dx, dy, nx, row0, nrows, A0, A2, A4, nimg=None, flags=None, order=4,
@@ -247,31 +256,34 @@ def map_deal_device(s, q, rho, Gamma, x0, y0, dx, dy, nx, row0, nrows, period, s
 
 
 def models_chi2_device(s, q, rho, Gamma, u0, alpha, M, tau0, dtau, T, flux, weight, stats, order=4, stream=None,
-                       device=None):
+                       device=None, segment=0):
     ctx = _capi.context(device)
     ctx.check(ctx.lib.mlm_models_chi2(ctx.handle, _p(s), _p(q), _p(rho), _p(Gamma), _p(u0), _p(alpha), M, tau0, dtau, T,
-                                      order, _p(flux), _p(weight), _p(stats), _p(stream)), "mlm_models_chi2")
+                                      order, int(segment), _p(flux), _p(weight), _p(stats), _p(stream)), "mlm_models_chi2")
 
 
 def models_times_device(s, q, rho, Gamma, u0, alpha, t0, tE, M, times, T, A0, A2, A4, nimg=None, flags=None, order=4,
-                        stream=None, device=None):
+                        stream=None, device=None, segment=0):
     """Model grid at observation times (device arrays; t0 / tE may be None = 0 / 1)."""
     ctx = _capi.context(device)
     ctx.check(ctx.lib.mlm_models_times(ctx.handle, _p(s), _p(q), _p(rho), _p(Gamma), _p(u0), _p(alpha), _p(t0), _p(tE), M,
-                                       _p(times), T, order, _p(A0), _p(A2), _p(A4), _p(nimg), _p(flags), _p(stream)),
+                                       _p(times), T, order, int(segment), _p(A0), _p(A2), _p(A4), _p(nimg), _p(flags),
+                                       _p(stream)),
               "mlm_models_times")
 
 
 def models_chi2_times_device(s, q, rho, Gamma, u0, alpha, t0, tE, M, times, T, flux, weight, stats, order=4, stream=None,
-                             device=None):
+                             device=None, segment=0):
     ctx = _capi.context(device)
     ctx.check(ctx.lib.mlm_models_chi2_times(ctx.handle, _p(s), _p(q), _p(rho), _p(Gamma), _p(u0), _p(alpha), _p(t0), _p(tE),
-                                            M, _p(times), T, order, _p(flux), _p(weight), _p(stats), _p(stream)),
+                                            M, _p(times), T, order, int(segment), _p(flux), _p(weight), _p(stats),
+                                            _p(stream)),
               "mlm_models_chi2_times")
 
 
 def models_device(s, q, rho, Gamma, u0, alpha, M, tau0, dtau, T, A0, A2, A4, nimg=None, flags=None, order=4,
-                  stream=None, device=None):
+                  stream=None, device=None, segment=0):
+    """segment = 0: the library picks it from M and T of THIS call (mlm_auto_segment)."""
     ctx = _capi.context(device)
     ctx.check(ctx.lib.mlm_models(ctx.handle, _p(s), _p(q), _p(rho), _p(Gamma), _p(u0), _p(alpha), M, tau0, dtau, T,
-                                 order, _p(A0), _p(A2), _p(A4), _p(nimg), _p(flags), _p(stream)), "mlm_models")
+                                 order, int(segment), _p(A0), _p(A2), _p(A4), _p(nimg), _p(flags), _p(stream)), "mlm_models")

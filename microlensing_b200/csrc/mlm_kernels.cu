@@ -10,6 +10,7 @@
 //
 // Reference interfaces replaced: see include/mlmultipoles.h.
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 
 #include <atomic>
 #include <cmath>
@@ -25,7 +26,7 @@
 // count what a kernel executes): every MLM_COUNT(event) of mlm_core.cuh adds the number of active lanes to
 // g_mlm_cnt[0][event] and 1 to g_mlm_cnt[1][event] (one atomic pair per warp-level event).
 #define MLM_CNT_NAMES(X) X(positions) X(laguerre_evals) X(newton_evals) X(lens_evals) X(track_fallbacks) X(cold_solves) \
-    X(classify_calls) X(classify_newton) X(nonphys_checks) X(images) X(quadratics)
+    X(classify_calls) X(classify_newton) X(nonphys_checks) X(images) X(quadratics) X(anchor_positions)
 enum {
 #define X(n) MLM_CNT_##n,
     MLM_CNT_NAMES(X)
@@ -76,11 +77,14 @@ __device__ __forceinline__ void store_result(const PointResult& r, int64_t i, do
 // entries that are far from their predecessor (> 0.02 Einstein radii), or whose tracking is
 // rejected, are solved cold, so an unordered list costs one cold solve per entry.  seg is a function of n
 // only; the 16-byte loads of a warp are seg entries apart (sector-granular, the path is compute-bound).
+// `perm` (optional): the list is visited in the order perm[0], perm[1], ... (mlm_points_unordered: the entries sorted
+// along a space-filling curve, so that consecutive visits are neighbours in the source plane); loads and stores go
+// to the entries' own places.
 template <int ORDER>
 __global__ void __launch_bounds__(MLM_BLOCK, 4)
 k_points(const __grid_constant__ LensTable T, const SourceFactors sf, const double2* __restrict__ zeta, int64_t n,
-         int seg, double* __restrict__ A0, double* __restrict__ A2, double* __restrict__ A4,
-         uint8_t* __restrict__ nimg, uint8_t* __restrict__ flags) {
+         int seg, const uint32_t* __restrict__ perm, double* __restrict__ A0, double* __restrict__ A2,
+         double* __restrict__ A4, uint8_t* __restrict__ nimg, uint8_t* __restrict__ flags) {
     __shared__ cd s_roots[2][5][MLM_BLOCK];
     cd* const sz = &s_roots[0][0][threadIdx.x];
     cd* const szp = &s_roots[1][0][threadIdx.x];
@@ -90,7 +94,8 @@ k_points(const __grid_constant__ LensTable T, const SourceFactors sf, const doub
     TrackState st;
     st.hist = 0; st.nimg = 0; st.extra = 0;
     cd zprev = mk(0.0, 0.0), dprev = mk(0.0, 0.0);
-    for (int64_t i = i0; i < i1; ++i) {
+    for (int64_t iv = i0; iv < i1; ++iv) {
+        const int64_t i = perm ? (int64_t)__ldg(perm + iv) : iv;
         const double2 zz = __ldg(zeta + i);
         const cd zt = mk(zz.x, zz.y);
         const cd d = zt - zprev;
@@ -116,6 +121,72 @@ k_points(const __grid_constant__ LensTable T, const SourceFactors sf, const doub
     }
 }
 
+// Unordered lists (mlm_points_unordered): bounding box, Morton keys of the positions on a 65536 x 65536 grid over
+// the box, radix sort of (key, index) -- CUB, library plumbing -- and k_points along the sorted order.
+__device__ __forceinline__ unsigned long long dbl_ordered(double v) {      // order-preserving map double -> uint64
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double ordered_dbl(unsigned long long u) {
+    const unsigned long long b = (u & 0x8000000000000000ull) ? (u & 0x7fffffffffffffffull) : ~u;
+    return __longlong_as_double((long long)b);
+}
+
+// bbox[0..3] = ordered(min x), ordered(max x), ordered(min y), ordered(max y); non-finite coordinates are ignored
+__global__ void k_bbox(const double2* __restrict__ zeta, int64_t n, unsigned long long* __restrict__ bbox) {
+    unsigned long long lo_x = ~0ull, hi_x = 0ull, lo_y = ~0ull, hi_y = 0ull;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        const double2 z = __ldg(zeta + i);
+        if (isfinite(z.x) && isfinite(z.y)) {
+            const unsigned long long ux = dbl_ordered(z.x), uy = dbl_ordered(z.y);
+            lo_x = ux < lo_x ? ux : lo_x; hi_x = ux > hi_x ? ux : hi_x;
+            lo_y = uy < lo_y ? uy : lo_y; hi_y = uy > hi_y ? uy : hi_y;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long t;
+        t = __shfl_down_sync(0xffffffffu, lo_x, o); lo_x = t < lo_x ? t : lo_x;
+        t = __shfl_down_sync(0xffffffffu, hi_x, o); hi_x = t > hi_x ? t : hi_x;
+        t = __shfl_down_sync(0xffffffffu, lo_y, o); lo_y = t < lo_y ? t : lo_y;
+        t = __shfl_down_sync(0xffffffffu, hi_y, o); hi_y = t > hi_y ? t : hi_y;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(bbox + 0, lo_x); atomicMax(bbox + 1, hi_x);
+        atomicMin(bbox + 2, lo_y); atomicMax(bbox + 3, hi_y);
+    }
+}
+
+__device__ __forceinline__ uint32_t spread16(uint32_t v) {               // 16 bits -> every second bit
+    v &= 0xffffu;
+    v = (v | (v << 8)) & 0x00ff00ffu;
+    v = (v | (v << 4)) & 0x0f0f0f0fu;
+    v = (v | (v << 2)) & 0x33333333u;
+    v = (v | (v << 1)) & 0x55555555u;
+    return v;
+}
+
+__global__ void __launch_bounds__(256) k_morton(const double2* __restrict__ zeta, int64_t n,
+                                                const unsigned long long* __restrict__ bbox,
+                                                uint32_t* __restrict__ keys, uint32_t* __restrict__ idx) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const double x_lo = ordered_dbl(bbox[0]), x_hi = ordered_dbl(bbox[1]);
+    const double y_lo = ordered_dbl(bbox[2]), y_hi = ordered_dbl(bbox[3]);
+    // one square cell size for both axes (distances matter, not the aspect ratio of the box)
+    const double ext = fmax(fmax(x_hi - x_lo, y_hi - y_lo), 1e-300);
+    const double sc = 65535.0 / ext;
+    const double2 z = __ldg(zeta + i);
+    uint32_t key = 0xffffffffu;                                           // non-finite entries last
+    if (isfinite(z.x) && isfinite(z.y)) {
+        const uint32_t cx = (uint32_t)fmin(fmax((z.x - x_lo) * sc, 0.0), 65535.0);
+        const uint32_t cy = (uint32_t)fmin(fmax((z.y - y_lo) * sc, 0.0), 65535.0);
+        key = spread16(cx) | (spread16(cy) << 1);
+    }
+    keys[i] = key;
+    idx[i] = (uint32_t)i;
+}
+
 // K1b: magnification map, zeta generated in-kernel (no input traffic).
 // blockIdx.x tiles the columns; blockIdx.y strides over STRIPS of `strip` consecutive rows
 // (aligned to absolute row numbers, so any row-sharding on multiples of `strip` reproduces the
@@ -128,11 +199,52 @@ k_points(const __grid_constant__ LensTable T, const SourceFactors sf, const doub
 // `period` strips, and the launch owns the positions sel[0..nsel) of every round (period = 1, nsel = 1:
 // all strips; period = world, sel = {rank}: cyclic sharding; unequal nsel per rank: weighted sharding,
 // e.g. the gather root takes more strips because its results do not cross NVLink).
+// ANCHORS: the roots at the first row of every owned strip, found by tracking ALONG that row (k_anchor, a small
+// launch before k_map): a thread walks `aseg` consecutive columns of one anchor row, so only one pixel in `aseg` is a
+// cold solve (Laguerre + deflation, ~3000 FP64 instructions against ~400 for a tracked step without the image sums).
+// k_map then starts its strips from the stored roots.  Segments are aligned to absolute column numbers and anchor rows
+// to absolute strip numbers, so sharding does not change a bit.  Layout: roots[(ii * 5 + k) * nx + col] (double2),
+// meta[ii * nx + col] = flags | nimg << 8 | extra << 11 | valid << 13, ii = ownership-relative strip index of the launch.
+#define MLM_ANCHOR_VALID 0x2000u
+__global__ void __launch_bounds__(MLM_BLOCK, MLM_MAP_MINBLOCKS)
+k_anchor(const __grid_constant__ LensTable T, double x0, double y0, double dx, double dy, double shift, int64_t nx,
+         int64_t row0, int strip, const __grid_constant__ Deal deal, int64_t i_count, int aseg,
+         double2* __restrict__ roots, uint16_t* __restrict__ meta) {
+    __shared__ cd s_roots[3][5][MLM_BLOCK];
+    cd* const sz = &s_roots[0][0][threadIdx.x];
+    cd* const szp = &s_roots[1][0][threadIdx.x];
+    cd* const szpp = &s_roots[2][0][threadIdx.x];
+    const int64_t c0 = ((int64_t)blockIdx.x * MLM_BLOCK + threadIdx.x) * aseg;
+    if (c0 >= nx) return;
+    const int64_t c1 = (c0 + aseg < nx) ? c0 + aseg : nx;
+    for (int64_t ii = blockIdx.y; ii < i_count; ii += gridDim.y) {
+        const int64_t k = deal_strip(deal, deal.t0 + ii);
+        const int64_t ra = (k * strip > row0) ? k * strip : row0;
+        const double y = __dadd_rn(y0, __dmul_rn((double)ra + 0.5, dy));
+        TrackState st;
+        st.hist = 0; st.nimg = 0; st.extra = 0;
+        for (int64_t c = c0; c < c1; ++c) {
+            const double x = __dadd_rn(__dadd_rn(x0, __dmul_rn((double)c + 0.5, dx)), -shift);
+            unsigned fl = 0;
+            MLM_COUNT(anchor_positions);
+            advance_images(T, mk(x, y), sz, szp, szpp, MLM_BLOCK, st, fl);
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                const cd zj = sz[j * MLM_BLOCK];
+                roots[(ii * 5 + j) * nx + c] = make_double2(zj.x, zj.y);
+            }
+            meta[ii * nx + c] = (uint16_t)((fl & 0xffu) | ((unsigned)st.nimg << 8) | ((unsigned)(st.extra & 3) << 11) |
+                                           (st.hist >= 1 ? MLM_ANCHOR_VALID : 0u));
+        }
+    }
+}
+
 template <int ORDER>
 __global__ void __launch_bounds__(MLM_BLOCK, MLM_MAP_MINBLOCKS)
 k_map(const __grid_constant__ LensTable T, const SourceFactors sf, double x0, double y0, double dx, double dy,
       double shift, int64_t nx, int64_t row0, int64_t nrows, int strip, const __grid_constant__ Deal deal,
-      int64_t i_count, int64_t i_axis, double* __restrict__ A0,
+      int64_t i_count, int64_t i_axis, const double2* __restrict__ aroots, const uint16_t* __restrict__ ameta,
+      double* __restrict__ A0,
       double* __restrict__ A2, double* __restrict__ A4, uint8_t* __restrict__ nimg, uint8_t* __restrict__ flags) {
     // root store of this thread: current and previous roots, [k][thread] so that a warp touches
     // 512 contiguous bytes per k (conflict-free); keeps 20 doubles out of the register file
@@ -160,26 +272,42 @@ k_map(const __grid_constant__ LensTable T, const SourceFactors sf, double x0, do
         const int64_t rb = ((k + 1) * strip < row0 + nrows) ? (k + 1) * strip : row0 + nrows;
         TrackState st;
         st.hist = 0; st.nimg = 0; st.extra = 0;
+        // the strip starts from its anchor (roots found by k_anchor at exactly this pixel) when there is one
+        unsigned anchor = 0;
+        if (ameta != nullptr) {
+            anchor = __ldg(ameta + ii * nx + col);
+            if (anchor & MLM_ANCHOR_VALID) {
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    const double2 zj = __ldg(aroots + (ii * 5 + j) * nx + col);
+                    sz[j * MLM_BLOCK] = mk(zj.x, zj.y);
+                }
+                st.hist = 1; st.nimg = (int)((anchor >> 8) & 7u); st.extra = (int)((anchor >> 11) & 3u);
+            }
+        }
         for (int64_t r = ra; r < rb; ++r) {
             const double y = __dadd_rn(y0, __dmul_rn((double)r + 0.5, dy));
             const cd zeta = mk(x, y);
             PointResult res;
             res.flags = 0;
             MLM_COUNT(positions);
-            advance_images(T, zeta, sz, szp, szpp, MLM_BLOCK, st, res.flags);
+            if (r == ra && (anchor & MLM_ANCHOR_VALID)) res.flags = anchor & 0xffu;     // the anchor IS this pixel's solution
+            else advance_images(T, zeta, sz, szp, szpp, MLM_BLOCK, st, res.flags);
             sum_images<ORDER>(T, sf, sz, MLM_BLOCK, st.nimg, res);
             store_result(res, (r - row0) * nx + col, A0, A2, A4, nimg, flags);
         }
     }
 }
 
-// K1c: batched model grid / light curves.  blockIdx.y strides over models; the block stages that
-// model's table in shared memory.  Each thread owns a SEGMENT of `seg` consecutive epochs of the
-// straight trajectory and walks along it with warm-started root tracking (cold solve at the
-// segment start and wherever tracking is rejected), exactly like a map column in k_map.
-// seg depends only on the number of epochs, so sharding the models over ranks does not change
-// a single bit of any model's light curve.
+// K1c: batched model grid / light curves.  Each thread owns a SEGMENT of `seg` consecutive epochs of a model's
+// straight trajectory and walks along it with warm-started root tracking (cold solve at the segment start and
+// wherever tracking is rejected), exactly like a map column in k_map.  A block of 64 threads serves G models at a
+// time, P = 64 / G threads each (P = 64 when a light curve has 64 segments or more, else the next power of two >=
+// the number of segments: short light curves of a big grid share a block instead of leaving lanes idle); the
+// models' tables sit in shared memory.  seg is an argument of the call (like the strip length of a map): the bits
+// of a light curve depend on it, not on how the grid is sharded over ranks.
 #define MLM_MODELS_BLOCK 64
+#define MLM_MODELS_GMAX 16                            /* models per block: P >= 4 threads per model */
 
 // Epochs of the light curves of a model grid: tau_t = tau0 + t dtau (uniform grid, times == NULL) or
 // tau_t = (times[t] - t0[m]) / tE[m] (observation times; t0, tE per model, NULL = 0 and 1).
@@ -213,36 +341,49 @@ __device__ __forceinline__ double epoch_ratio(const Epochs& ep, double tau, doub
     return ratio;
 }
 
+// per-model constants of a block's models (shared memory)
+struct ModelSlot {
+    LensTable T;
+    SourceFactors sf;
+    double ca, sa, shift;                              // cos(alpha), sin(alpha), s q / (1 + q)
+};
+
+__device__ __forceinline__ void stage_model(ModelSlot* slot, const double* s, const double* q, const double* rho,
+                                            const double* Gamma, const double* alpha, int64_t m) {
+    const double sm = s[m], qm = q[m];
+    make_table(sm, qm, &slot->T);
+    slot->sf = source_factors(rho[m], Gamma[m]);
+    double sa, ca;
+    sincos(alpha[m], &sa, &ca);
+    slot->ca = ca; slot->sa = sa; slot->shift = sm * qm / (1.0 + qm);
+}
+
 template <int ORDER>
 __global__ void __launch_bounds__(MLM_MODELS_BLOCK, 6)
 k_models(const double* __restrict__ s, const double* __restrict__ q, const double* __restrict__ rho,
          const double* __restrict__ Gamma, const double* __restrict__ u0, const double* __restrict__ alpha,
-         int64_t M, const Epochs ep, int64_t Tn, int seg, double* __restrict__ A0,
+         int64_t M, const Epochs ep, int64_t Tn, int seg, int P, double* __restrict__ A0,
          double* __restrict__ A2, double* __restrict__ A4, uint8_t* __restrict__ nimg, uint8_t* __restrict__ flags) {
-    __shared__ LensTable T;
-    __shared__ SourceFactors sf;
-    __shared__ double rot[3];                          // cos(alpha), sin(alpha), shift
+    __shared__ ModelSlot slots[MLM_MODELS_GMAX];
     __shared__ cd s_roots[3][5][MLM_MODELS_BLOCK];
     cd* const sz = &s_roots[0][0][threadIdx.x];
     cd* const szp = &s_roots[1][0][threadIdx.x];
     cd* const szpp = &s_roots[2][0][threadIdx.x];
     const int64_t nseg = (Tn + seg - 1) / seg;
-    for (int64_t m = blockIdx.y; m < M; m += gridDim.y) {
+    const int G = MLM_MODELS_BLOCK / P;                // models per block
+    const int g = threadIdx.x / P, lane = threadIdx.x % P;
+    const int64_t nmb = (M + G - 1) / G;               // model groups
+    for (int64_t mb = blockIdx.y; mb < nmb; mb += gridDim.y) {
         __syncthreads();
-        if (threadIdx.x == 0) {
-            const double sm = s[m], qm = q[m];
-            make_table(sm, qm, &T);
-            sf = source_factors(rho[m], Gamma[m]);
-            double sa, ca;
-            sincos(alpha[m], &sa, &ca);
-            rot[0] = ca; rot[1] = sa; rot[2] = sm * qm / (1.0 + qm);
-        }
+        if (threadIdx.x < G && mb * G + threadIdx.x < M) stage_model(&slots[threadIdx.x], s, q, rho, Gamma, alpha, mb * G + threadIdx.x);
         __syncthreads();
+        const int64_t m = mb * G + g;
+        if (m >= M) continue;
+        const ModelSlot& ms = slots[g];
         const double u = u0[m];
-        const double ur1 = __dmul_rn(u, rot[1]), ur0 = __dmul_rn(u, rot[0]);
+        const double ur1 = __dmul_rn(u, ms.sa), ur0 = __dmul_rn(u, ms.ca);
         const double t0m = ep.t0 ? ep.t0[m] : 0.0, tEm = ep.tE ? ep.tE[m] : 1.0;
-        for (int64_t sg = (int64_t)blockIdx.x * MLM_MODELS_BLOCK + threadIdx.x; sg < nseg;
-             sg += (int64_t)gridDim.x * MLM_MODELS_BLOCK) {
+        for (int64_t sg = (int64_t)blockIdx.x * P + lane; sg < nseg; sg += (int64_t)gridDim.x * P) {
             const int64_t t0 = sg * seg;
             const int64_t t1 = (t0 + seg < Tn) ? t0 + seg : Tn;
             TrackState st;
@@ -255,104 +396,103 @@ k_models(const double* __restrict__ s, const double* __restrict__ q, const doubl
                 const double tau = epoch_tau(ep, t, t0m, tEm);
                 const double ratio = epoch_ratio(ep, tau, tau_prev, dt_prev, st);
                 // zeta_cm = (tau + i u0) (cos a + i sin a), then shift to the primary frame
-                const double zx = __dadd_rn(__dadd_rn(__dmul_rn(tau, rot[0]), -ur1), -rot[2]);
-                const double zy = __dadd_rn(__dmul_rn(tau, rot[1]), ur0);
+                const double zx = __dadd_rn(__dadd_rn(__dmul_rn(tau, ms.ca), -ur1), -ms.shift);
+                const double zy = __dadd_rn(__dmul_rn(tau, ms.sa), ur0);
                 const cd zeta = mk(zx, zy);
                 PointResult res;
                 res.flags = 0;
                 MLM_COUNT(positions);
-                advance_images(T, zeta, sz, szp, szpp, MLM_MODELS_BLOCK, st, res.flags, ratio);
-                sum_images<ORDER>(T, sf, sz, MLM_MODELS_BLOCK, st.nimg, res);
+                advance_images(ms.T, zeta, sz, szp, szpp, MLM_MODELS_BLOCK, st, res.flags, ratio);
+                sum_images<ORDER>(ms.T, ms.sf, sz, MLM_MODELS_BLOCK, st.nimg, res);
                 store_result(res, m * Tn + t, A0, A2, A4, nimg, flags);
             }
         }
     }
 }
 
-// K1d: model grid with the light-curve fit fused in.  One block = one model: the
-// threads walk their segments of the model light curve exactly like k_models, but instead of storing
-// the magnifications they accumulate the weighted sums of the linear flux fit F_t = Fs A_t + Fb
-// against observed fluxes f_t with weights w_t = 1/sigma_t^2; a fixed-order block reduction makes
-// the result deterministic.  Output per model (8 doubles):
+// K1d: model grid with the light-curve fit fused in.  The P threads of a model walk their
+// segments of the model light curve exactly like k_models, but instead of storing the magnifications they
+// accumulate the weighted sums of the linear flux fit F_t = Fs A_t + Fb against observed fluxes f_t with weights
+// w_t = 1/sigma_t^2; a fixed-order tree reduction over the P threads makes the result deterministic.  Output per
+// model (8 doubles):
 //   chi2 (minimised over Fs, Fb), Fs, Fb, sum w A, sum w A^2, sum w A f, #epochs with 5 images, #flagged epochs
 template <int ORDER>
 __global__ void __launch_bounds__(MLM_MODELS_BLOCK, 6)
 k_models_chi2(const double* __restrict__ s, const double* __restrict__ q, const double* __restrict__ rho,
               const double* __restrict__ Gamma, const double* __restrict__ u0, const double* __restrict__ alpha,
-              int64_t M, const Epochs ep, int64_t Tn, int seg, const double* __restrict__ flux,
+              int64_t M, const Epochs ep, int64_t Tn, int seg, int P, const double* __restrict__ flux,
               const double* __restrict__ weight, double* __restrict__ stats) {
-    __shared__ LensTable T;
-    __shared__ SourceFactors sf;
-    __shared__ double rot[3];
+    __shared__ ModelSlot slots[MLM_MODELS_GMAX];
     __shared__ cd s_roots[3][5][MLM_MODELS_BLOCK];
     __shared__ double s_red[8][MLM_MODELS_BLOCK];
     cd* const sz = &s_roots[0][0][threadIdx.x];
     cd* const szp = &s_roots[1][0][threadIdx.x];
     cd* const szpp = &s_roots[2][0][threadIdx.x];
     const int64_t nseg = (Tn + seg - 1) / seg;
-    for (int64_t m = blockIdx.x; m < M; m += gridDim.x) {
+    const int G = MLM_MODELS_BLOCK / P;
+    const int g = threadIdx.x / P, lane = threadIdx.x % P;
+    const int64_t nmb = (M + G - 1) / G;
+    for (int64_t mb = blockIdx.x; mb < nmb; mb += gridDim.x) {
         __syncthreads();
-        if (threadIdx.x == 0) {
-            const double sm = s[m], qm = q[m];
-            make_table(sm, qm, &T);
-            sf = source_factors(rho[m], Gamma[m]);
-            double sa, ca;
-            sincos(alpha[m], &sa, &ca);
-            rot[0] = ca; rot[1] = sa; rot[2] = sm * qm / (1.0 + qm);
-        }
+        if (threadIdx.x < G && mb * G + threadIdx.x < M) stage_model(&slots[threadIdx.x], s, q, rho, Gamma, alpha, mb * G + threadIdx.x);
         __syncthreads();
-        const double u = u0[m];
-        const double ur1 = __dmul_rn(u, rot[1]), ur0 = __dmul_rn(u, rot[0]);
-        const double t0m = ep.t0 ? ep.t0[m] : 0.0, tEm = ep.tE ? ep.tE[m] : 1.0;
+        const int64_t m = mb * G + g;
         double a_w = 0.0, a_wa = 0.0, a_waa = 0.0, a_wf = 0.0, a_waf = 0.0, a_wff = 0.0, a_n5 = 0.0, a_nf = 0.0;
-        for (int64_t sg = threadIdx.x; sg < nseg; sg += MLM_MODELS_BLOCK) {
-            const int64_t t0 = sg * seg;
-            const int64_t t1 = (t0 + seg < Tn) ? t0 + seg : Tn;
-            TrackState st;
-            st.hist = 0; st.nimg = 0; st.extra = 0;
-            double tau_prev = 0.0, dt_prev = 1.0;
-            for (int64_t t = t0; t < t1; ++t) {
-                asm volatile("" ::: "memory");
-                const double tau = epoch_tau(ep, t, t0m, tEm);
-                const double ratio = epoch_ratio(ep, tau, tau_prev, dt_prev, st);
-                const double zx = __dadd_rn(__dadd_rn(__dmul_rn(tau, rot[0]), -ur1), -rot[2]);
-                const double zy = __dadd_rn(__dmul_rn(tau, rot[1]), ur0);
-                const cd zeta = mk(zx, zy);
-                PointResult res;
-                res.flags = 0;
-                MLM_COUNT(positions);
-                advance_images(T, zeta, sz, szp, szpp, MLM_MODELS_BLOCK, st, res.flags, ratio);
-                sum_images<ORDER>(T, sf, sz, MLM_MODELS_BLOCK, st.nimg, res);
-                const double A = (ORDER >= 4) ? res.A4 : res.A2;
-                const double w = __ldg(weight + t), f = __ldg(flux + t);
-                const double wa = w * A;
-                a_w += w; a_wa += wa; a_waa = fma(wa, A, a_waa);
-                a_wf = fma(w, f, a_wf); a_waf = fma(wa, f, a_waf); a_wff = fma(w * f, f, a_wff);
-                a_n5 += (res.nimg == 5) ? 1.0 : 0.0;
-                a_nf += (res.flags != 0) ? 1.0 : 0.0;
+        if (m < M) {
+            const ModelSlot& ms = slots[g];
+            const double u = u0[m];
+            const double ur1 = __dmul_rn(u, ms.sa), ur0 = __dmul_rn(u, ms.ca);
+            const double t0m = ep.t0 ? ep.t0[m] : 0.0, tEm = ep.tE ? ep.tE[m] : 1.0;
+            for (int64_t sg = lane; sg < nseg; sg += P) {
+                const int64_t t0 = sg * seg;
+                const int64_t t1 = (t0 + seg < Tn) ? t0 + seg : Tn;
+                TrackState st;
+                st.hist = 0; st.nimg = 0; st.extra = 0;
+                double tau_prev = 0.0, dt_prev = 1.0;
+                for (int64_t t = t0; t < t1; ++t) {
+                    asm volatile("" ::: "memory");
+                    const double tau = epoch_tau(ep, t, t0m, tEm);
+                    const double ratio = epoch_ratio(ep, tau, tau_prev, dt_prev, st);
+                    const double zx = __dadd_rn(__dadd_rn(__dmul_rn(tau, ms.ca), -ur1), -ms.shift);
+                    const double zy = __dadd_rn(__dmul_rn(tau, ms.sa), ur0);
+                    const cd zeta = mk(zx, zy);
+                    PointResult res;
+                    res.flags = 0;
+                    MLM_COUNT(positions);
+                    advance_images(ms.T, zeta, sz, szp, szpp, MLM_MODELS_BLOCK, st, res.flags, ratio);
+                    sum_images<ORDER>(ms.T, ms.sf, sz, MLM_MODELS_BLOCK, st.nimg, res);
+                    const double A = (ORDER >= 4) ? res.A4 : res.A2;
+                    const double w = __ldg(weight + t), f = __ldg(flux + t);
+                    const double wa = w * A;
+                    a_w += w; a_wa += wa; a_waa = fma(wa, A, a_waa);
+                    a_wf = fma(w, f, a_wf); a_waf = fma(wa, f, a_waf); a_wff = fma(w * f, f, a_wff);
+                    a_n5 += (res.nimg == 5) ? 1.0 : 0.0;
+                    a_nf += (res.flags != 0) ? 1.0 : 0.0;
+                }
             }
         }
-        // fixed-order tree reduction over the block
+        // fixed-order tree reduction over the P threads of every model of the block
         s_red[0][threadIdx.x] = a_w;  s_red[1][threadIdx.x] = a_wa;  s_red[2][threadIdx.x] = a_waa;
         s_red[3][threadIdx.x] = a_wf; s_red[4][threadIdx.x] = a_waf; s_red[5][threadIdx.x] = a_wff;
         s_red[6][threadIdx.x] = a_n5; s_red[7][threadIdx.x] = a_nf;
         __syncthreads();
-        for (int o = MLM_MODELS_BLOCK / 2; o > 0; o >>= 1) {
-            if (threadIdx.x < o) {
+        for (int o = P / 2; o > 0; o >>= 1) {
+            if (lane < o) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) s_red[k][threadIdx.x] += s_red[k][threadIdx.x + o];
             }
             __syncthreads();
         }
-        if (threadIdx.x == 0) {
-            const double S = s_red[0][0], SA = s_red[1][0], SAA = s_red[2][0], SF = s_red[3][0], SAF = s_red[4][0],
-                         SFF = s_red[5][0];
+        if (lane == 0 && m < M) {
+            const int b = threadIdx.x;
+            const double S = s_red[0][b], SA = s_red[1][b], SAA = s_red[2][b], SF = s_red[3][b], SAF = s_red[4][b],
+                         SFF = s_red[5][b];
             const double det = S * SAA - SA * SA;
             const double Fs = (S * SAF - SA * SF) / det;
             const double Fb = (SAA * SF - SA * SAF) / det;
             double* o = stats + 8 * m;
             o[0] = SFF - Fs * SAF - Fb * SF;
-            o[1] = Fs; o[2] = Fb; o[3] = SA; o[4] = SAA; o[5] = SAF; o[6] = s_red[6][0]; o[7] = s_red[7][0];
+            o[1] = Fs; o[2] = Fb; o[3] = SA; o[4] = SAA; o[5] = SAF; o[6] = s_red[6][b]; o[7] = s_red[7][b];
         }
     }
 }
@@ -488,6 +628,7 @@ struct mlm_context {
     // partial sums): two host threads may share a context.  Device-pointer entry points only enqueue on the
     // caller's stream and touch no context state.
     std::recursive_mutex mu;
+    int anchor_segment = 16;                           // columns per thread of k_anchor (MLM_MAP_ANCHOR; 0: no anchors, cold strip starts)
     int points_segment = 0;                            // consecutive list entries per thread of k_points (0: from n; MLM_POINTS_SEGMENT)
     int models_segment = 0;                            // epochs per warm-start segment of k_models (0: from T; MLM_SEGMENT)
 };
@@ -583,6 +724,18 @@ int mlm_create(int device, mlm_context** out) {
     if (const char* e2 = getenv("MLM_MAP_STRIP")) {
         const int v = atoi(e2);
         if (v >= 1 && v <= 4096) ctx->map_strip_env = v;
+    }
+    if (const char* e5 = getenv("MLM_MAP_ANCHOR")) {
+        const int v = atoi(e5);
+        if (v >= 0 && v <= 4096) ctx->anchor_segment = v;
+    }
+    {   // the anchors live in stream-ordered allocations (cudaMallocAsync): keep the pool's memory across synchronisations
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
     }
     if (const char* e4 = getenv("MLM_POINTS_SEGMENT")) {
         const int v = atoi(e4);
@@ -762,11 +915,63 @@ int mlm_points(mlm_context* ctx, double s, double q, double rho, double Gamma, c
     const unsigned blocks = (unsigned)((nthreads + MLM_BLOCK - 1) / MLM_BLOCK);
     cudaStream_t st = pick(ctx, stream);
     if (order == 4)
-        k_points<4><<<blocks, MLM_BLOCK, 0, st>>>(T, sf, (const double2*)zeta, n, seg, A0, A2, A4, nimg, flags);
+        k_points<4><<<blocks, MLM_BLOCK, 0, st>>>(T, sf, (const double2*)zeta, n, seg, nullptr, A0, A2, A4, nimg, flags);
     else
-        k_points<2><<<blocks, MLM_BLOCK, 0, st>>>(T, sf, (const double2*)zeta, n, seg, A0, A2, A4, nimg, flags);
+        k_points<2><<<blocks, MLM_BLOCK, 0, st>>>(T, sf, (const double2*)zeta, n, seg, nullptr, A0, A2, A4, nimg, flags);
     ctx->launches++;
     CK(cudaGetLastError());
+    return 0;
+}
+
+int mlm_points_unordered(mlm_context* ctx, double s, double q, double rho, double Gamma, const double* zeta, int64_t n,
+                         int order, double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags, void* stream) {
+    if (!ctx) return fail(ctx, MLM_EINVAL, "mlm_points_unordered: NULL context");
+    if (n < 0 || n > 0xffffffffll || (order != 2 && order != 4) || bad_lens(s, q))
+        return fail(ctx, MLM_EINVAL, "mlm_points_unordered: bad argument");
+    if (n == 0) return 0;
+    if (!zeta || !(A0 || A2 || A4 || nimg || flags)) return fail(ctx, MLM_EINVAL, "mlm_points_unordered: NULL buffer");
+    if (n < 4096) return mlm_points(ctx, s, q, rho, Gamma, zeta, n, order, A0, A2, A4, nimg, flags, stream);
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = pick(ctx, stream);
+    // stream-ordered scratch: bbox | keys in/out | indices in/out | CUB temporary storage
+    size_t cub_bytes = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                       (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, 0, 32, st));
+    const size_t npad = ((size_t)n + 63) & ~(size_t)63;
+    char* ws = nullptr;
+    CK(cudaMallocAsync((void**)&ws, 256 + 4 * npad * sizeof(uint32_t) + cub_bytes, st));
+    unsigned long long* bbox = (unsigned long long*)ws;
+    uint32_t* keys = (uint32_t*)(ws + 256);
+    uint32_t* keys_out = keys + npad;
+    uint32_t* idx = keys_out + npad;
+    uint32_t* perm = idx + npad;
+    void* cub_ws = perm + npad;
+    const unsigned long long init[4] = {~0ull, 0ull, ~0ull, 0ull};
+    cudaError_t e = cudaMemcpyAsync(bbox, init, sizeof(init), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        const unsigned nb = (unsigned)((n + 255) / 256);
+        k_bbox<<<nb < 1184u ? nb : 1184u, 256, 0, st>>>((const double2*)zeta, n, bbox);
+        k_morton<<<nb, 256, 0, st>>>((const double2*)zeta, n, bbox, keys, idx);
+        ctx->launches += 2;
+        e = cub::DeviceRadixSort::SortPairs(cub_ws, cub_bytes, keys, keys_out, idx, perm, (int)n, 0, 32, st);
+    }
+    if (e == cudaSuccess) {
+        LensTable T;
+        make_table(s, q, &T);
+        const SourceFactors sf = source_factors(rho, Gamma);
+        // runs of 8 sorted entries per thread: neighbours along the curve are tracked, a run start is a cold solve
+        const int seg = ctx->points_segment > 0 ? ctx->points_segment : 8;
+        const int64_t nthreads = (n + seg - 1) / seg;
+        const unsigned blocks = (unsigned)((nthreads + MLM_BLOCK - 1) / MLM_BLOCK);
+        if (order == 4)
+            k_points<4><<<blocks, MLM_BLOCK, 0, st>>>(T, sf, (const double2*)zeta, n, seg, perm, A0, A2, A4, nimg, flags);
+        else
+            k_points<2><<<blocks, MLM_BLOCK, 0, st>>>(T, sf, (const double2*)zeta, n, seg, perm, A0, A2, A4, nimg, flags);
+        ctx->launches++;
+        e = cudaGetLastError();
+    }
+    cudaFreeAsync(ws, st);
+    if (e != cudaSuccess) return fail(ctx, (int)e, "mlm_points_unordered");
     return 0;
 }
 
@@ -814,14 +1019,36 @@ int mlm_map_deal(mlm_context* ctx, double s, double q, double rho, double Gamma,
     }
     dim3 grid((unsigned)((nx + MLM_BLOCK - 1) / MLM_BLOCK), (unsigned)(i_count < 65535 ? i_count : 65535));
     cudaStream_t st = pick(ctx, stream);
+    // anchors of the owned strips (stream-ordered scratch: 82 bytes per anchor pixel); strips of one or two rows are
+    // not worth it, and without the scratch the strips simply start cold
+    double2* aroots = nullptr;
+    uint16_t* ameta = nullptr;
+    void* ws = nullptr;
+    const int aseg = ctx->anchor_segment;
+    if (aseg > 0 && strip >= 4 && nx >= 2 * (int64_t)aseg) {
+        const size_t npix = (size_t)i_count * (size_t)nx;
+        if (cudaMallocAsync(&ws, npix * 82 + 256, st) == cudaSuccess) {
+            aroots = (double2*)ws;
+            ameta = (uint16_t*)((char*)ws + npix * 80);
+            const int64_t nseg = (nx + aseg - 1) / aseg;
+            dim3 ga((unsigned)((nseg + MLM_BLOCK - 1) / MLM_BLOCK), grid.y);
+            k_anchor<<<ga, MLM_BLOCK, 0, st>>>(T, x0, y0, dx, dy, shift, nx, row0, strip, deal, i_count, aseg, aroots, ameta);
+            ctx->launches++;
+        } else {
+            cudaGetLastError();
+            ws = nullptr;
+        }
+    }
     if (order == 4)
         k_map<4><<<grid, MLM_BLOCK, 0, st>>>(T, sf, x0, y0, dx, dy, shift, nx, row0, nrows, strip, deal, i_count, i_axis,
-                                              A0, A2, A4, nimg, flags);
+                                              aroots, ameta, A0, A2, A4, nimg, flags);
     else
         k_map<2><<<grid, MLM_BLOCK, 0, st>>>(T, sf, x0, y0, dx, dy, shift, nx, row0, nrows, strip, deal, i_count, i_axis,
-                                              A0, A2, A4, nimg, flags);
+                                              aroots, ameta, A0, A2, A4, nimg, flags);
     ctx->launches++;
-    CK(cudaGetLastError());
+    cudaError_t le = cudaGetLastError();
+    if (ws) cudaFreeAsync(ws, st);
+    if (le != cudaSuccess) return fail(ctx, (int)le, "k_map launch");
     return 0;
 }
 
@@ -842,73 +1069,100 @@ int mlm_map(mlm_context* ctx, double s, double q, double rho, double Gamma, doub
                         flags, stream);
 }
 
-static int models_segment(mlm_context* ctx, int64_t Tn);
+static int models_segment(mlm_context* ctx, int seg, int64_t M, int64_t Tn);
+static int models_threads_per_model(int64_t Tn, int seg);
 
 static int launch_models(mlm_context* ctx, const char* who, const double* s, const double* q, const double* rho,
                          const double* Gamma, const double* u0, const double* alpha, int64_t M, const Epochs& ep,
-                         int64_t Tn, int order, double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags,
+                         int64_t Tn, int order, int seg, double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags,
                          void* stream) {
     if (!ctx) return fail(ctx, MLM_EINVAL, who);
-    if (M < 0 || Tn < 0 || (order != 2 && order != 4)) return fail(ctx, MLM_EINVAL, who);
+    if (M < 0 || Tn < 0 || (order != 2 && order != 4) || seg < 0 || seg > 65536) return fail(ctx, MLM_EINVAL, who);
     if (M == 0 || Tn == 0) return 0;
     if (!s || !q || !rho || !Gamma || !u0 || !alpha || !(A0 || A2 || A4 || nimg || flags)) return fail(ctx, MLM_EINVAL, who);
     DeviceGuard g(ctx->device);
-    const int seg = models_segment(ctx, Tn);
+    seg = models_segment(ctx, seg, M, Tn);
+    const int P = models_threads_per_model(Tn, seg);
     const int64_t nseg = (Tn + seg - 1) / seg;
-    int64_t bx = (nseg + MLM_MODELS_BLOCK - 1) / MLM_MODELS_BLOCK;
+    int64_t bx = (nseg + P - 1) / P;
     if (bx > 4096) bx = 4096;
-    dim3 grid((unsigned)bx, (unsigned)(M < 65535 ? M : 65535));
+    const int64_t nmb = (M + MLM_MODELS_BLOCK / P - 1) / (MLM_MODELS_BLOCK / P);
+    dim3 grid((unsigned)bx, (unsigned)(nmb < 65535 ? nmb : 65535));
     cudaStream_t st = pick(ctx, stream);
     if (order == 4)
-        k_models<4><<<grid, MLM_MODELS_BLOCK, 0, st>>>(s, q, rho, Gamma, u0, alpha, M, ep, Tn, seg, A0, A2, A4, nimg, flags);
+        k_models<4><<<grid, MLM_MODELS_BLOCK, 0, st>>>(s, q, rho, Gamma, u0, alpha, M, ep, Tn, seg, P, A0, A2, A4, nimg, flags);
     else
-        k_models<2><<<grid, MLM_MODELS_BLOCK, 0, st>>>(s, q, rho, Gamma, u0, alpha, M, ep, Tn, seg, A0, A2, A4, nimg, flags);
+        k_models<2><<<grid, MLM_MODELS_BLOCK, 0, st>>>(s, q, rho, Gamma, u0, alpha, M, ep, Tn, seg, P, A0, A2, A4, nimg, flags);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;
 }
 
 int mlm_models(mlm_context* ctx, const double* s, const double* q, const double* rho, const double* Gamma,
-               const double* u0, const double* alpha, int64_t M, double tau0, double dtau, int64_t Tn, int order,
+               const double* u0, const double* alpha, int64_t M, double tau0, double dtau, int64_t Tn, int order, int seg,
                double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags, void* stream) {
     const Epochs ep = {tau0, dtau, nullptr, nullptr, nullptr};
-    return launch_models(ctx, "mlm_models: bad argument", s, q, rho, Gamma, u0, alpha, M, ep, Tn, order, A0, A2, A4, nimg,
-                         flags, stream);
+    return launch_models(ctx, "mlm_models: bad argument", s, q, rho, Gamma, u0, alpha, M, ep, Tn, order, seg, A0, A2, A4,
+                         nimg, flags, stream);
 }
 
 int mlm_models_times(mlm_context* ctx, const double* s, const double* q, const double* rho, const double* Gamma,
                      const double* u0, const double* alpha, const double* t0, const double* tE, int64_t M,
-                     const double* times, int64_t Tn, int order, double* A0, double* A2, double* A4, uint8_t* nimg,
+                     const double* times, int64_t Tn, int order, int seg, double* A0, double* A2, double* A4, uint8_t* nimg,
                      uint8_t* flags, void* stream) {
     if (Tn > 0 && !times) return fail(ctx, MLM_EINVAL, "mlm_models_times: NULL times");
     const Epochs ep = {0.0, 0.0, times, t0, tE};
-    return launch_models(ctx, "mlm_models_times: bad argument", s, q, rho, Gamma, u0, alpha, M, ep, Tn, order, A0, A2, A4,
-                         nimg, flags, stream);
+    return launch_models(ctx, "mlm_models_times: bad argument", s, q, rho, Gamma, u0, alpha, M, ep, Tn, order, seg, A0, A2,
+                         A4, nimg, flags, stream);
 }
 
-static int models_segment(mlm_context* ctx, int64_t Tn) {
-    // epochs per warm-start segment: a function of Tn only (see k_models)
-    int seg = ctx->models_segment > 0 ? ctx->models_segment : (int)((Tn + MLM_MODELS_BLOCK - 1) / MLM_MODELS_BLOCK);
-    if (ctx->models_segment <= 0) seg = seg < 4 ? 4 : (seg > 32 ? 32 : seg);
-    return seg;
+// Epochs per warm-start segment for a grid of M models x Tn epochs: long segments (few cold solves: one per
+// segment, ~2.5 tracked epochs each) as long as the grid still fills the GPU about twice (sm_count x 6 blocks x 64
+// threads resident), between 4 and 128 epochs.
+static int auto_segment(int sm_count, int64_t M, int64_t Tn) {
+    const int64_t resident = (int64_t)sm_count * 6 * MLM_MODELS_BLOCK;
+    int64_t seg = (M * Tn + 2 * resident - 1) / (2 * resident);
+    if (seg > Tn) seg = Tn;
+    return (int)(seg < 4 ? 4 : (seg > 128 ? 128 : seg));
+}
+
+static int models_segment(mlm_context* ctx, int seg, int64_t M, int64_t Tn) {
+    if (seg > 0) return seg;
+    if (ctx->models_segment > 0) return ctx->models_segment;          // MLM_SEGMENT (experiments)
+    return auto_segment(ctx->sm_count, M, Tn);
+}
+
+// threads of a block that share one model: 64, or the next power of two >= the number of segments (>= 4)
+static int models_threads_per_model(int64_t Tn, int seg) {
+    const int64_t nseg = (Tn + seg - 1) / seg;
+    int P = MLM_MODELS_BLOCK / MLM_MODELS_GMAX;
+    while (P < MLM_MODELS_BLOCK && P < nseg) P *= 2;
+    return P;
+}
+
+int mlm_auto_segment(mlm_context* ctx, int64_t M, int64_t Tn) {
+    if (!ctx || M < 0 || Tn < 0) return MLM_EINVAL;
+    return auto_segment(ctx->sm_count, M > 0 ? M : 1, Tn > 0 ? Tn : 1);
 }
 
 static int launch_models_chi2(mlm_context* ctx, const char* who, const double* s, const double* q, const double* rho,
                               const double* Gamma, const double* u0, const double* alpha, int64_t M, const Epochs& ep,
-                              int64_t Tn, int order, const double* flux, const double* weight, double* stats,
+                              int64_t Tn, int order, int seg, const double* flux, const double* weight, double* stats,
                               void* stream) {
     if (!ctx) return fail(ctx, MLM_EINVAL, who);
-    if (M < 0 || Tn < 0 || (order != 2 && order != 4)) return fail(ctx, MLM_EINVAL, who);
+    if (M < 0 || Tn < 0 || (order != 2 && order != 4) || seg < 0 || seg > 65536) return fail(ctx, MLM_EINVAL, who);
     if (M == 0) return 0;
     if (!s || !q || !rho || !Gamma || !u0 || !alpha || !stats || (Tn > 0 && (!flux || !weight))) return fail(ctx, MLM_EINVAL, who);
     DeviceGuard g(ctx->device);
-    const int seg = models_segment(ctx, Tn);
-    const unsigned blocks = (unsigned)(M < 1048576 ? M : 1048576);
+    seg = models_segment(ctx, seg, M, Tn);
+    const int P = models_threads_per_model(Tn, seg);
+    const int64_t nmb = (M + MLM_MODELS_BLOCK / P - 1) / (MLM_MODELS_BLOCK / P);
+    const unsigned blocks = (unsigned)(nmb < 1048576 ? nmb : 1048576);
     cudaStream_t st = pick(ctx, stream);
     if (order == 4)
-        k_models_chi2<4><<<blocks, MLM_MODELS_BLOCK, 0, st>>>(s, q, rho, Gamma, u0, alpha, M, ep, Tn, seg, flux, weight, stats);
+        k_models_chi2<4><<<blocks, MLM_MODELS_BLOCK, 0, st>>>(s, q, rho, Gamma, u0, alpha, M, ep, Tn, seg, P, flux, weight, stats);
     else
-        k_models_chi2<2><<<blocks, MLM_MODELS_BLOCK, 0, st>>>(s, q, rho, Gamma, u0, alpha, M, ep, Tn, seg, flux, weight, stats);
+        k_models_chi2<2><<<blocks, MLM_MODELS_BLOCK, 0, st>>>(s, q, rho, Gamma, u0, alpha, M, ep, Tn, seg, P, flux, weight, stats);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -916,25 +1170,25 @@ static int launch_models_chi2(mlm_context* ctx, const char* who, const double* s
 
 int mlm_models_chi2(mlm_context* ctx, const double* s, const double* q, const double* rho, const double* Gamma,
                     const double* u0, const double* alpha, int64_t M, double tau0, double dtau, int64_t Tn, int order,
-                    const double* flux, const double* weight, double* stats, void* stream) {
+                    int seg, const double* flux, const double* weight, double* stats, void* stream) {
     const Epochs ep = {tau0, dtau, nullptr, nullptr, nullptr};
-    return launch_models_chi2(ctx, "mlm_models_chi2: bad argument", s, q, rho, Gamma, u0, alpha, M, ep, Tn, order, flux,
-                              weight, stats, stream);
+    return launch_models_chi2(ctx, "mlm_models_chi2: bad argument", s, q, rho, Gamma, u0, alpha, M, ep, Tn, order, seg,
+                              flux, weight, stats, stream);
 }
 
 int mlm_models_chi2_times(mlm_context* ctx, const double* s, const double* q, const double* rho, const double* Gamma,
                           const double* u0, const double* alpha, const double* t0, const double* tE, int64_t M,
-                          const double* times, int64_t Tn, int order, const double* flux, const double* weight,
+                          const double* times, int64_t Tn, int order, int seg, const double* flux, const double* weight,
                           double* stats, void* stream) {
     if (Tn > 0 && !times) return fail(ctx, MLM_EINVAL, "mlm_models_chi2_times: NULL times");
     const Epochs ep = {0.0, 0.0, times, t0, tE};
     return launch_models_chi2(ctx, "mlm_models_chi2_times: bad argument", s, q, rho, Gamma, u0, alpha, M, ep, Tn, order,
-                              flux, weight, stats, stream);
+                              seg, flux, weight, stats, stream);
 }
 
 // host variant of both: npar = 6 (uniform epochs) or 8 (+ t0, tE) parameter arrays, times optional
 static int models_chi2_host_impl(mlm_context* ctx, const char* who, const double* const* hp, int npar, int64_t M,
-                                 double tau0, double dtau, const double* times, int64_t Tn, int order,
+                                 double tau0, double dtau, const double* times, int64_t Tn, int order, int seg,
                                  const double* flux, const double* weight, double* stats) {
     if (!ctx) return fail(ctx, MLM_EINVAL, who);
     if (M < 0 || Tn < 0 || (order != 2 && order != 4)) return fail(ctx, MLM_EINVAL, who);
@@ -962,7 +1216,7 @@ static int models_chi2_host_impl(mlm_context* ctx, const char* who, const double
     const Epochs ep = {tau0, dtau, times ? dtimes : nullptr, npar == 8 ? par + 6 * mpad : nullptr,
                        npar == 8 ? par + 7 * mpad : nullptr};
     rc = launch_models_chi2(ctx, who, par, par + mpad, par + 2 * mpad, par + 3 * mpad, par + 4 * mpad, par + 5 * mpad, M,
-                            ep, Tn, order, dflux, dw, dstats, st);
+                            ep, Tn, order, seg, dflux, dw, dstats, st);
     if (rc) return rc;
     CK(cudaMemcpyAsync(stats, dstats, (size_t)M * 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -971,20 +1225,20 @@ static int models_chi2_host_impl(mlm_context* ctx, const char* who, const double
 
 int mlm_models_chi2_host(mlm_context* ctx, const double* s, const double* q, const double* rho, const double* Gamma,
                          const double* u0, const double* alpha, int64_t M, double tau0, double dtau, int64_t Tn,
-                         int order, const double* flux, const double* weight, double* stats) {
+                         int order, int seg, const double* flux, const double* weight, double* stats) {
     const double* hp[6] = {s, q, rho, Gamma, u0, alpha};
-    return models_chi2_host_impl(ctx, "mlm_models_chi2_host: bad argument", hp, 6, M, tau0, dtau, nullptr, Tn, order, flux,
-                                 weight, stats);
+    return models_chi2_host_impl(ctx, "mlm_models_chi2_host: bad argument", hp, 6, M, tau0, dtau, nullptr, Tn, order, seg,
+                                 flux, weight, stats);
 }
 
 int mlm_models_chi2_times_host(mlm_context* ctx, const double* s, const double* q, const double* rho,
                                const double* Gamma, const double* u0, const double* alpha, const double* t0,
-                               const double* tE, int64_t M, const double* times, int64_t Tn, int order,
+                               const double* tE, int64_t M, const double* times, int64_t Tn, int order, int seg,
                                const double* flux, const double* weight, double* stats) {
     if (Tn > 0 && !times) return fail(ctx, MLM_EINVAL, "mlm_models_chi2_times_host: NULL times");
     const double* hp[8] = {s, q, rho, Gamma, u0, alpha, t0, tE};
     return models_chi2_host_impl(ctx, "mlm_models_chi2_times_host: bad argument", hp, 8, M, 0.0, 0.0, times, Tn, order,
-                                 flux, weight, stats);
+                                 seg, flux, weight, stats);
 }
 
 int mlm_from_wk(mlm_context* ctx, const double* Wk, int64_t n, int order, double rho, double Gamma, double* out,
@@ -1084,6 +1338,19 @@ static int d2h_chunk(mlm_context* ctx, const Scratch& sc, int64_t off, int64_t c
 
 #define MLM_CHUNK_POINTS (int64_t(1) << 21)
 
+// Does a host list have spatial order?  Fraction of sampled consecutive pairs within 0.02 Einstein radii.
+static bool host_list_is_coherent(const double* zeta, int64_t n) {
+    if (n < 8192) return true;                         // small lists: the plain path (no sort) is as fast
+    const int64_t samples = 2048, stride = (n - 1) / samples;
+    int64_t close = 0;
+    for (int64_t k = 0; k < samples; ++k) {
+        const int64_t i = k * stride;
+        const double dx = zeta[2 * i + 2] - zeta[2 * i], dy = zeta[2 * i + 3] - zeta[2 * i + 1];
+        if (dx * dx + dy * dy <= 4e-4) ++close;
+    }
+    return 2 * close >= samples;
+}
+
 int mlm_points_host(mlm_context* ctx, double s, double q, double rho, double Gamma, const double* zeta, int64_t n,
                     int order, double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags) {
     if (!ctx) return fail(ctx, MLM_EINVAL, "mlm_points_host: NULL context");
@@ -1117,11 +1384,14 @@ int mlm_points_host(mlm_context* ctx, double s, double q, double rho, double Gam
     // chunks alternate between the two streams: H2D(k+1) and D2H(k-1) overlap kernel(k)
     int k = 0;
     const int64_t chunk = (n / 8 > MLM_CHUNK_POINTS) ? (n + 7) / 8 : MLM_CHUNK_POINTS;   // at most ~8 chunks
+    // a list without spatial order is visited along a space-filling curve (each chunk sorted on the device)
+    const bool coherent = host_list_is_coherent(zeta, n);
     for (int64_t off = 0; off < n; off += chunk, ++k) {
         const int64_t cnt = (n - off < chunk) ? (n - off) : chunk;
         cudaStream_t st = ctx->stream[k & 1];
         CK(cudaMemcpyAsync(sc.zeta + 2 * off, zeta + 2 * off, cnt * 16, cudaMemcpyHostToDevice, st));
-        rc = mlm_points(ctx, s, q, rho, Gamma, sc.zeta + 2 * off, cnt, order, A0 ? sc.A0 + off : nullptr,
+        rc = (coherent ? mlm_points : mlm_points_unordered)(
+                        ctx, s, q, rho, Gamma, sc.zeta + 2 * off, cnt, order, A0 ? sc.A0 + off : nullptr,
                         A2 ? sc.A2 + off : nullptr, A4 ? sc.A4 + off : nullptr, nimg ? sc.nimg + off : nullptr,
                         flags ? sc.flags + off : nullptr, st);
         if (rc) return rc;
@@ -1177,11 +1447,12 @@ int mlm_map_host(mlm_context* ctx, double s, double q, double rho, double Gamma,
 }
 
 static int models_host_impl(mlm_context* ctx, const char* who, const double* const* hp, int npar, int64_t M,
-                            double tau0, double dtau, const double* times, int64_t Tn, int order, double* A0,
+                            double tau0, double dtau, const double* times, int64_t Tn, int order, int seg, double* A0,
                             double* A2, double* A4, uint8_t* nimg, uint8_t* flags) {
     if (!ctx) return fail(ctx, MLM_EINVAL, who);
-    if (M < 0 || Tn < 0 || (order != 2 && order != 4)) return fail(ctx, MLM_EINVAL, who);
+    if (M < 0 || Tn < 0 || (order != 2 && order != 4) || seg < 0 || seg > 65536) return fail(ctx, MLM_EINVAL, who);
     if (M == 0 || Tn == 0) return 0;
+    seg = models_segment(ctx, seg, M, Tn);             // from the WHOLE grid: the chunks below must not change a bit
     for (int i = 0; i < npar; ++i)
         if (!hp[i]) return fail(ctx, MLM_EINVAL, who);
     if (!(A0 || A2 || A4 || nimg || flags)) return fail(ctx, MLM_EINVAL, who);
@@ -1213,7 +1484,7 @@ static int models_host_impl(mlm_context* ctx, const char* who, const double* con
         const Epochs ep = {tau0, dtau, times ? dtimes : nullptr, npar == 8 ? par + 6 * mpad + m0 : nullptr,
                            npar == 8 ? par + 7 * mpad + m0 : nullptr};
         rc = launch_models(ctx, who, par + m0, par + mpad + m0, par + 2 * mpad + m0, par + 3 * mpad + m0,
-                           par + 4 * mpad + m0, par + 5 * mpad + m0, nm, ep, Tn, order, A0 ? sc.A0 + off : nullptr,
+                           par + 4 * mpad + m0, par + 5 * mpad + m0, nm, ep, Tn, order, seg, A0 ? sc.A0 + off : nullptr,
                            A2 ? sc.A2 + off : nullptr, A4 ? sc.A4 + off : nullptr, nimg ? sc.nimg + off : nullptr,
                            flags ? sc.flags + off : nullptr, st);
         if (rc) return rc;
@@ -1227,20 +1498,20 @@ static int models_host_impl(mlm_context* ctx, const char* who, const double* con
 
 int mlm_models_host(mlm_context* ctx, const double* s, const double* q, const double* rho, const double* Gamma,
                     const double* u0, const double* alpha, int64_t M, double tau0, double dtau, int64_t Tn, int order,
-                    double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags) {
+                    int seg, double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags) {
     const double* hp[6] = {s, q, rho, Gamma, u0, alpha};
-    return models_host_impl(ctx, "mlm_models_host: bad argument", hp, 6, M, tau0, dtau, nullptr, Tn, order, A0, A2, A4, nimg,
-                            flags);
+    return models_host_impl(ctx, "mlm_models_host: bad argument", hp, 6, M, tau0, dtau, nullptr, Tn, order, seg, A0, A2, A4,
+                            nimg, flags);
 }
 
 int mlm_models_times_host(mlm_context* ctx, const double* s, const double* q, const double* rho, const double* Gamma,
                           const double* u0, const double* alpha, const double* t0, const double* tE, int64_t M,
-                          const double* times, int64_t Tn, int order, double* A0, double* A2, double* A4, uint8_t* nimg,
-                          uint8_t* flags) {
+                          const double* times, int64_t Tn, int order, int seg, double* A0, double* A2, double* A4,
+                          uint8_t* nimg, uint8_t* flags) {
     if (Tn > 0 && !times) return fail(ctx, MLM_EINVAL, "mlm_models_times_host: NULL times");
     const double* hp[8] = {s, q, rho, Gamma, u0, alpha, t0, tE};
-    return models_host_impl(ctx, "mlm_models_times_host: bad argument", hp, 8, M, 0.0, 0.0, times, Tn, order, A0, A2, A4,
-                            nimg, flags);
+    return models_host_impl(ctx, "mlm_models_times_host: bad argument", hp, 8, M, 0.0, 0.0, times, Tn, order, seg, A0, A2,
+                            A4, nimg, flags);
 }
 
 int mlm_from_wk_host(mlm_context* ctx, const double* Wk, int64_t n, int order, double rho, double Gamma, double* out) {

@@ -542,9 +542,11 @@ class SharedHostMap:
                     self._registered.append((a, b))
         if world > 1:
             import torch.distributed as dist
-            dist.barrier(group=group)
+            dist.barrier(group=group)      # every rank has opened and mapped the file
         if rank == 0:
             os.unlink(self.path)           # the mappings keep the memory alive; nothing is left behind in /dev/shm
+        if world > 1:
+            dist.barrier(group=group)      # ... and nobody returns before the name is gone
 
     def own_rows(self):
         """{key: (hi-lo, nx) view} of the rows this rank owns."""
@@ -612,14 +614,15 @@ class ShardedModels:
                directly they would travel 8 bytes at a time -- measured 2x SLOWER at 8 GPUs than 1).
     fit=(flux, sigma): the light-curve fit is fused into the kernel (mlm_models_chi2); only 8 doubles per
                model travel.
-    A model's light curve does not depend on which rank computes it (the segment length of the kernel
-    is a function of T only), so the result is bit-identical to the single-GPU one.
+    A model's light curve does not depend on which rank computes it: the segment length of the kernel (`segment`,
+    default mlm_auto_segment of the WHOLE grid) is the same on every rank, so the result is bit-identical to the
+    single-GPU one computed with that segment.
     """
 
     STAT_KEYS = ("chi2", "Fs", "Fb", "SA", "SAA", "SAF", "n5", "nflag")
 
     def __init__(self, params, tau0: float = 0.0, dtau: float = 0.0, T: int = 0, rank: int = 0, world: int = 1,
-                 device=None, group=None, outputs=None, fit=None, times=None):
+                 device=None, group=None, outputs=None, fit=None, times=None, segment: int | None = None):
         import numpy as np
         import torch
         import torch.distributed as dist
@@ -640,6 +643,8 @@ class ShardedModels:
         self.M = arrs[0].size
         self.lo, self.hi = shard_range(self.M, rank, world)
         self.par = [torch.from_numpy(a[self.lo:self.hi].copy()).to(self.device) for a in arrs]
+        # epochs per tracking segment: from the WHOLE grid, the same on every rank (the bits of a light curve depend on it)
+        self.segment = int(segment) if segment else _capi.context(self.device.index).auto_segment(self.M, self.T)
         self.outputs = tuple(k for k, _ in KEYS) if outputs is None else tuple(outputs)
         self.fit = None
         ctx = _capi.context(self.device.index)
@@ -699,18 +704,20 @@ class ShardedModels:
 
         def run(par, nm, A0, A2, A4, ni, fl):
             if self.times is None:
-                models_device(*par, nm, self.tau0, self.dtau, self.T, A0, A2, A4, ni, fl, order=order, stream=st, device=dev)
+                models_device(*par, nm, self.tau0, self.dtau, self.T, A0, A2, A4, ni, fl, order=order, stream=st, device=dev,
+                              segment=self.segment)
             else:
-                models_times_device(*par, nm, self.times, self.T, A0, A2, A4, ni, fl, order=order, stream=st, device=dev)
+                models_times_device(*par, nm, self.times, self.T, A0, A2, A4, ni, fl, order=order, stream=st, device=dev,
+                                    segment=self.segment)
 
         if m:
             if self.fit is not None:
                 if self.times is None:
                     models_chi2_device(*self.par, m, self.tau0, self.dtau, self.T, self.fit[0], self.fit[1],
-                                       base + self.lo * 64, order=order, stream=st, device=dev)
+                                       base + self.lo * 64, order=order, stream=st, device=dev, segment=self.segment)
                 else:
                     models_chi2_times_device(*self.par, m, self.times, self.T, self.fit[0], self.fit[1],
-                                             base + self.lo * 64, order=order, stream=st, device=dev)
+                                             base + self.lo * 64, order=order, stream=st, device=dev, segment=self.segment)
             elif self.local is None:
                 ptr = {key: (base + self.layout[key] + self.lo * self.T * item if key in self.outputs else None)
                        for key, item in KEYS}

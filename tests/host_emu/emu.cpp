@@ -3,7 +3,7 @@
 // recursion) against the oracle without a GPU.  Never loaded by microlensing_b200.
 #ifdef MLM_STATS
 static long g_cnt_laguerre_evals = 0, g_cnt_newton_evals = 0, g_cnt_track_fallbacks = 0, g_cnt_lens_evals = 0;
-static long g_cnt_cold_solves = 0, g_cnt_classify_calls = 0, g_cnt_classify_newton = 0, g_cnt_nonphys_checks = 0, g_cnt_images = 0, g_cnt_quadratics = 0;
+static long g_cnt_cold_solves = 0, g_cnt_classify_calls = 0, g_cnt_classify_newton = 0, g_cnt_nonphys_checks = 0, g_cnt_images = 0, g_cnt_quadratics = 0, g_cnt_anchor_positions = 0;
 #define MLM_COUNT(name) (++g_cnt_##name)
 #endif
 #include "../../microlensing_b200/csrc/mlm_core.cuh"
@@ -14,6 +14,12 @@ using namespace mlm;
 extern "C" {
 #ifdef MLM_STATS
 void emu_stats(long* out, int reset) { out[0] = g_cnt_laguerre_evals; out[1] = g_cnt_newton_evals; out[2] = g_cnt_lens_evals; out[3] = g_cnt_track_fallbacks; if (reset) g_cnt_laguerre_evals = g_cnt_newton_evals = g_cnt_lens_evals = g_cnt_track_fallbacks = 0; }
+// all counters: laguerre, newton, lens, fallbacks, cold_solves, classify_calls, classify_newton, nonphys_checks, images, quadratics
+void emu_stats_all(long* out, int reset) {
+    long* p[10] = {&g_cnt_laguerre_evals, &g_cnt_newton_evals, &g_cnt_lens_evals, &g_cnt_track_fallbacks, &g_cnt_cold_solves,
+                   &g_cnt_classify_calls, &g_cnt_classify_newton, &g_cnt_nonphys_checks, &g_cnt_images, &g_cnt_quadratics};
+    for (int i = 0; i < 10; ++i) { out[i] = *p[i]; if (reset) *p[i] = 0; }
+}
 #endif
 
 

@@ -239,6 +239,56 @@ def test_points_on_an_uneven_curved_trajectory(mb, s, q):
     assert np.abs(rs["A4"] / r["A4"][perm] - 1)[ok].max() < 1e-9
 
 
+def test_unordered_list_is_visited_along_a_space_filling_curve(mb):
+    """mlm_points_unordered (what magnification_points picks for a list without spatial order): Morton-sorted visiting
+    order with the images carried between neighbours, results at the entries' own places.  Against the plain path (one
+    cold solve per entry) on the same list, and against the oracle on a sample."""
+    import torch
+    from oracle import cassan_oracle as oracle
+    from microlensing_b200.batched import points_device
+    rng = np.random.default_rng(2718)
+    for (s, q, rho, G, n, win) in ((1.0, 0.5, 1e-3, 0.5, 60000, 1.5), (0.9, 1e-3, 1e-3, 0.5, 40000, 0.6)):
+        zeta = rng.uniform(-win, win, n) + 1j * rng.uniform(-win, win, n)
+        zeta[17] = zeta[4711]                                          # duplicates are fine
+        auto = mb.magnification_points(s, q, rho, G, zeta)            # >= 8192 entries without order -> sorted path
+        dev = torch.device("cuda", torch.cuda.current_device())
+        zt = torch.from_numpy(zeta).to(dev)
+        b = [torch.empty(n, dtype=torch.float64, device=dev) for _ in range(3)] + \
+            [torch.empty(n, dtype=torch.uint8, device=dev) for _ in range(2)]
+        st = torch.cuda.current_stream().cuda_stream
+        res = {}
+        for unordered in (False, True):
+            for t in b:
+                t.fill_(0)
+            points_device(s, q, rho, G, zt, n, *b, stream=st, unordered=unordered)
+            torch.cuda.synchronize()
+            res[unordered] = [t.cpu().numpy().copy() for t in b]
+        plain, srt = res[False], res[True]
+        assert np.array_equal(auto["nimg"], srt[3]) and np.array_equal(auto["A4"], srt[2])      # the host API took the sorted path
+        assert np.array_equal(plain[3], srt[3])                        # image counts: tracked == cold
+        ok = (plain[4] == 0) & (srt[4] == 0)
+        for k in range(3):
+            assert np.abs(srt[k][ok] / plain[k][ok] - 1).max() < 1e-9, k
+        assert (srt[4] & 1).sum() == 0
+        idx = rng.choice(n, 4000, replace=False)
+        nb, B0, B2, B4, z, keep, minJ, resid = oracle.batch_a4(s, q, rho, G, zeta[idx], return_extra=True)
+        ref_A = np.stack([B0, B2, B4], 1)
+        rep = parity.compare(srt[3][idx], np.stack([srt[0][idx], srt[1][idx], srt[2][idx]], 1), nb, ref_A,
+                             parity.mask_from_reference(ref_A, resid, minJ), got_flags=srt[4][idx],
+                             truth_fn=truth_fn_factory([(s, q, rho, G)] * len(idx), zeta[idx]))
+        print("unordered list parity:", rep)
+    # non-finite entries do not disturb the others
+    zeta = rng.uniform(-1, 1, 9000) + 1j * rng.uniform(-1, 1, 9000)
+    good = mb.magnification_points(1.0, 0.5, 1e-3, 0.5, zeta)
+    zeta2 = zeta.copy()
+    zeta2[5] = complex(np.nan, 0.0)
+    bad = mb.magnification_points(1.0, 0.5, 1e-3, 0.5, zeta2)
+    keep = np.arange(9000) != 5
+    assert np.array_equal(bad["nimg"][keep], good["nimg"][keep])
+    ok = keep & (good["flags"] == 0) & (bad["flags"] == 0)
+    assert np.abs(bad["A4"][ok] / good["A4"][ok] - 1).max() < 1e-9
+
+
 def test_models_C5_sample_vs_oracle(mb):
     from oracle import cassan_oracle as oracle
     rng = np.random.default_rng(20240517)
@@ -308,6 +358,20 @@ def test_models_chi2_fused_fit(mb):
     # order 2 uses the quadrupole light curve
     r2 = mb.models_chi2(s, q, rho, G, u0, al, tau0, dtau, flux, sigma, order=2)
     assert np.allclose(r2["SA"], (w[None, :] * lc["A2"]).sum(axis=1), rtol=1e-10)
+    # long segments: 700 epochs in segments of 100 -> 8 threads per model, 8 models share a block of 64 threads
+    # (what a 1e4-model grid gets); same light curves to rounding, same statistics from them
+    assert mb._capi.context().auto_segment(10000, 2000) == 128 and mb._capi.context().auto_segment(1, 1000000) <= 16
+    for seg in (100, 350, 700):
+        lcs = mb.magnification_models(s, q, rho, G, u0, al, tau0, dtau, T, segment=seg)
+        assert np.array_equal(lcs["nimg"], lc["nimg"]), seg
+        ok = (lcs["flags"] == 0) & (lc["flags"] == 0)
+        assert np.abs(lcs["A4"] / lc["A4"] - 1)[ok].max() < 1e-9, seg
+        rs = mb.models_chi2(s, q, rho, G, u0, al, tau0, dtau, flux, sigma, segment=seg)
+        for m in range(M):
+            chi2, Fs, Fb, SA, SAA, SAF = fit(lcs["A4"][m])
+            assert np.allclose([rs["Fs"][m], rs["Fb"][m], rs["SA"][m], rs["SAA"][m], rs["SAF"][m]], [Fs, Fb, SA, SAA, SAF],
+                               rtol=1e-10), (seg, m)
+            assert rs["n5"][m] == (lcs["nimg"][m] == 5).sum() and rs["nflag"][m] == (lcs["flags"][m] != 0).sum()
 
 
 def test_models_at_observation_times(mb):
@@ -602,13 +666,21 @@ def _two_gpu_models_worker(rank, world, port, out_dir):
         sf = ShardedModels(par, -2.0, 4.0 / T, T, rank, world, fit=(flux, sigma))
         sf.compute()
         fit = sf.result_host()
+        s64 = ShardedModels(par, -2.0, 4.0 / T, T, rank, world, segment=64)      # 8 threads per model, 8 models per block
+        s64.compute()
+        res64 = s64.result_host()
+        f64 = ShardedModels(par, -2.0, 4.0 / T, T, rank, world, fit=(flux, sigma), segment=64)
+        f64.compute()
+        fit64 = f64.result_host()
+        s64.close(); f64.close()
         par8, times = _model_grid_times()
         st = ShardedModels(par8, rank=rank, world=world, times=times)
         st.compute()
         rt = st.result_host()
         if rank == 0:
             np.savez(os.path.join(out_dir, "models.npz"), **res, **{"fit_" + k: v for k, v in fit.items()},
-                     times_A4=rt["A4"], times_nimg=rt["nimg"])
+                     times_A4=rt["A4"], times_nimg=rt["nimg"], **{"s64_" + k: v for k, v in res64.items()},
+                     **{"f64_" + k: v for k, v in fit64.items()})
         dist.barrier()
         sm.close()
         sf.close()
@@ -655,6 +727,12 @@ def test_sharded_models_single_and_two_gpu(mb, tmp_path):
         assert np.array_equal(res[k], one[k]), k
     for k in ShardedModels.STAT_KEYS:
         assert np.array_equal(fit[k], fit1[k]), k
+    # a light curve does not depend on how many models share its call (host chunks, shards): model 5 alone, same segment
+    for seg in (4, 64):
+        full = mb.magnification_models(*par, -2.0, 4.0 / T, T, segment=seg)
+        alone = mb.magnification_models(*[a[5:6] for a in par], -2.0, 4.0 / T, T, segment=seg)
+        for k in ("A0", "A2", "A4", "nimg", "flags"):
+            assert np.array_equal(alone[k][0], full[k][5]), (seg, k)
     par8, times = _model_grid_times()
     onet = mb.magnification_models(*par8[:6], times=times, t0=par8[6], tE=par8[7])
     stt = ShardedModels(par8, times=times)
@@ -676,6 +754,13 @@ def test_sharded_models_single_and_two_gpu(mb, tmp_path):
     for k in ShardedModels.STAT_KEYS:
         assert np.array_equal(got["fit_" + k], fit1[k]), k
     assert np.array_equal(got["times_A4"], onet["A4"]) and np.array_equal(got["times_nimg"], onet["nimg"])
+    # ... and with long segments (several models per block), for which the sharded ranks see different model counts
+    one64 = mb.magnification_models(*par, -2.0, 4.0 / T, T, segment=64)
+    fit64 = mb.models_chi2(*par, -2.0, 4.0 / T, flux, sigma, segment=64)
+    for k in ("A0", "A2", "A4", "nimg", "flags"):
+        assert np.array_equal(got["s64_" + k], one64[k]), k
+    for k in ShardedModels.STAT_KEYS:
+        assert np.array_equal(got["f64_" + k], fit64[k]), k
 
 
 def test_full_size_properties(mb):
