@@ -116,7 +116,7 @@ int mlm_points(mlm_context* ctx, double s, double q, double rho, double Gamma,
                const double* zeta, int64_t n, int order,
                double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags, void* stream);
 /* The same for a list WITHOUT spatial order (random positions, a shuffled catalogue): the entries are visited along
- * a space-filling curve (Morton keys on a 65536^2 grid over their bounding box, radix-sorted on the device), so that
+ * a space-filling curve (Hilbert-curve keys on a 65536^2 grid over their bounding box, radix-sorted on the device), so that
  * consecutive visits are neighbours in the source plane and the images can be carried from one to the next instead of
  * a cold solve per entry; results land at the entries' own indices.  n < 2^32.  Worth it when fewer than about half of
  * the consecutive entries are within 0.02 Einstein radii of each other (mlm_points_host checks a sample and picks). */
@@ -242,6 +242,11 @@ int mlm_fp64_peak(mlm_context* ctx, double* tflops);
  * mode 1 = DFMA only, mode 2 = DFMA/DMUL/DADD 11:4:1; blocks_per_sm x 128 threads resident per SM.
  * Returns executed FP64 thread-instructions per second (nominal B200: 148 x 64 x 1.965e9 = 1.86e13). */
 int mlm_fp64_probe(mlm_context* ctx, int mode, int blocks_per_sm, double* inst_per_s);
+/* store-pattern probe: the store side of the map kernel without its arithmetic, into the given (possibly peer-mapped)
+ * arrays of nx x nrows positions; mode 0 = the five SoA arrays like the map kernel, 1 = float64 arrays only,
+ * 2 = uint8 arrays only, 3 = five arrays with the uint8 rows written 128 bytes at a time.  nx: multiple of 128. */
+int mlm_store_probe(mlm_context* ctx, int mode, int64_t nx, int64_t nrows, int rows_per_block, double* A0, double* A2,
+                    double* A4, uint8_t* nimg, uint8_t* flags, void* stream);
 /* static description of the fused kernel (registers per thread, spill bytes) from
  * cudaFuncGetAttributes: [0]=regs points<4>, [1]=local bytes points<4>, [2]=regs map<4>, [3]=local bytes map<4> */
 int mlm_kernel_info(mlm_context* ctx, int32_t* out, int n);

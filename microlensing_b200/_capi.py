@@ -64,6 +64,7 @@ SIGNATURES = {
     "mlm_akl_host": [_P, _P, _P, _P, _L, _P],
     "mlm_fp64_peak": [_P, ctypes.POINTER(_D)],
     "mlm_fp64_probe": [_P, _I, _I, ctypes.POINTER(_D)],
+    "mlm_store_probe": [_P, _I, _L, _L, _I, _P, _P, _P, _P, _P, _P],
     "mlm_kernel_info": [_P, ctypes.POINTER(ctypes.c_int32), _I],
     "mlm_stats_read": [_P, ctypes.POINTER(ctypes.c_uint64), _I, _I],
 }

@@ -80,11 +80,15 @@ __device__ __forceinline__ void store_result(const PointResult& r, int64_t i, do
 // `perm` (optional): the list is visited in the order perm[0], perm[1], ... (mlm_points_unordered: the entries sorted
 // along a space-filling curve, so that consecutive visits are neighbours in the source plane); loads and stores go
 // to the entries' own places.
+// perm_close / perm_need (with perm): the sorted order is used only if at least perm_need of the SAMPLED consecutive
+// pairs of it are neighbours (k_perm_check) -- a list too sparse for that is visited in its own order, cold.
 template <int ORDER>
 __global__ void __launch_bounds__(MLM_BLOCK, 4)
 k_points(const __grid_constant__ LensTable T, const SourceFactors sf, const double2* __restrict__ zeta, int64_t n,
-         int seg, const uint32_t* __restrict__ perm, double* __restrict__ A0, double* __restrict__ A2,
+         int seg, const uint32_t* __restrict__ perm, const unsigned* __restrict__ perm_close, unsigned perm_need,
+         double* __restrict__ A0, double* __restrict__ A2,
          double* __restrict__ A4, uint8_t* __restrict__ nimg, uint8_t* __restrict__ flags) {
+    if (perm != nullptr && perm_close != nullptr && __ldg(perm_close) < perm_need) perm = nullptr;
     __shared__ cd s_roots[2][5][MLM_BLOCK];
     cd* const sz = &s_roots[0][0][threadIdx.x];
     cd* const szp = &s_roots[1][0][threadIdx.x];
@@ -121,8 +125,8 @@ k_points(const __grid_constant__ LensTable T, const SourceFactors sf, const doub
     }
 }
 
-// Unordered lists (mlm_points_unordered): bounding box, Morton keys of the positions on a 65536 x 65536 grid over
-// the box, radix sort of (key, index) -- CUB, library plumbing -- and k_points along the sorted order.
+// Unordered lists (mlm_points_unordered): bounding box, Hilbert-curve keys of the positions on a 65536 x 65536 grid
+// over the box, radix sort of (key, index) -- CUB, library plumbing -- and k_points along the sorted order.
 __device__ __forceinline__ unsigned long long dbl_ordered(double v) {      // order-preserving map double -> uint64
     const unsigned long long b = (unsigned long long)__double_as_longlong(v);
     return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
@@ -151,22 +155,53 @@ __global__ void k_bbox(const double2* __restrict__ zeta, int64_t n, unsigned lon
         t = __shfl_down_sync(0xffffffffu, lo_y, o); lo_y = t < lo_y ? t : lo_y;
         t = __shfl_down_sync(0xffffffffu, hi_y, o); hi_y = t > hi_y ? t : hi_y;
     }
-    if ((threadIdx.x & 31) == 0) {
+    // one set of atomics per block, not per warp (tens of thousands of atomics on four addresses serialise)
+    __shared__ unsigned long long sh[4][8];
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { sh[0][w] = lo_x; sh[1][w] = hi_x; sh[2][w] = lo_y; sh[3][w] = hi_y; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < (int)(blockDim.x >> 5); ++k) {
+            lo_x = sh[0][k] < lo_x ? sh[0][k] : lo_x; hi_x = sh[1][k] > hi_x ? sh[1][k] : hi_x;
+            lo_y = sh[2][k] < lo_y ? sh[2][k] : lo_y; hi_y = sh[3][k] > hi_y ? sh[3][k] : hi_y;
+        }
         atomicMin(bbox + 0, lo_x); atomicMax(bbox + 1, hi_x);
         atomicMin(bbox + 2, lo_y); atomicMax(bbox + 3, hi_y);
     }
 }
 
-__device__ __forceinline__ uint32_t spread16(uint32_t v) {               // 16 bits -> every second bit
-    v &= 0xffffu;
-    v = (v | (v << 8)) & 0x00ff00ffu;
-    v = (v | (v << 4)) & 0x0f0f0f0fu;
-    v = (v | (v << 2)) & 0x33333333u;
-    v = (v | (v << 1)) & 0x55555555u;
-    return v;
+// index of cell (x, y) of a 65536 x 65536 grid along the Hilbert curve: consecutive indices are ADJACENT cells (a
+// Morton / Z-order curve jumps across the grid at every quadrant boundary, and every jump of more than 0.02 Einstein
+// radii is a cold solve of one lane that the other 31 wait for)
+__device__ __forceinline__ uint32_t hilbert16(uint32_t x, uint32_t y) {
+    uint32_t d = 0;
+#pragma unroll
+    for (uint32_t s = 1u << 15; s > 0; s >>= 1) {
+        const uint32_t rx = (x & s) ? 1u : 0u, ry = (y & s) ? 1u : 0u;
+        d += s * s * ((3u * rx) ^ ry);
+        if (ry == 0) {
+            if (rx == 1) { x = 65535u - x; y = 65535u - y; }
+            const uint32_t t = x; x = y; y = t;
+        }
+    }
+    return d;
 }
 
-__global__ void __launch_bounds__(256) k_morton(const double2* __restrict__ zeta, int64_t n,
+// every 8th consecutive pair of the sorted order: how many are within 0.01 Einstein radii of each other?
+__global__ void __launch_bounds__(256) k_perm_check(const double2* __restrict__ zeta, const uint32_t* __restrict__ perm,
+                                                    int64_t n, unsigned* __restrict__ close) {
+    const int64_t j = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 8;
+    unsigned c = 0;
+    if (j + 1 < n) {
+        const double2 a = __ldg(zeta + __ldg(perm + j)), b = __ldg(zeta + __ldg(perm + j + 1));
+        const double dx = b.x - a.x, dy = b.y - a.y;
+        c = (dx * dx + dy * dy <= 1e-4) ? 1u : 0u;
+    }
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(close, c);
+}
+
+__global__ void __launch_bounds__(256) k_curve_keys(const double2* __restrict__ zeta, int64_t n,
                                                 const unsigned long long* __restrict__ bbox,
                                                 uint32_t* __restrict__ keys, uint32_t* __restrict__ idx) {
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
@@ -181,7 +216,7 @@ __global__ void __launch_bounds__(256) k_morton(const double2* __restrict__ zeta
     if (isfinite(z.x) && isfinite(z.y)) {
         const uint32_t cx = (uint32_t)fmin(fmax((z.x - x_lo) * sc, 0.0), 65535.0);
         const uint32_t cy = (uint32_t)fmin(fmax((z.y - y_lo) * sc, 0.0), 65535.0);
-        key = spread16(cx) | (spread16(cy) << 1);
+        key = hilbert16(cx, cy);
     }
     keys[i] = key;
     idx[i] = (uint32_t)i;
@@ -566,6 +601,43 @@ k_akl(const double2* __restrict__ mu, const double2* __restrict__ W2, const doub
     out[i] = make_double2(a.x, a.y);
 }
 
+// Store-pattern probe (measurement only, tools/peer_store_probe.py): the store side of k_map without its arithmetic --
+// a block of 128 threads owns 128 columns and walks down `nrows` rows.  mode 0: the five SoA arrays exactly like
+// store_result (per warp and row 3 x 256 B + 2 x 32 B); 1: the three float64 arrays only; 2: the two uint8 arrays only;
+// 3: five arrays, the uint8 ones transposed through shared memory so that one warp writes 128 contiguous bytes per row.
+__global__ void __launch_bounds__(MLM_BLOCK) k_store_probe(int mode, int64_t nx, int64_t nrows, int rows_per_block,
+                                                           double* __restrict__ A0, double* __restrict__ A2,
+                                                           double* __restrict__ A4, uint8_t* __restrict__ nimg,
+                                                           uint8_t* __restrict__ flags) {
+    __shared__ uint8_t sb[2][4][MLM_BLOCK];
+    const int64_t col = (int64_t)blockIdx.x * MLM_BLOCK + threadIdx.x;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+    const int64_t r1 = (r0 + rows_per_block < nrows) ? r0 + rows_per_block : nrows;
+    if (col >= nx) return;                                   // nx is a multiple of 128 in the probe
+    for (int64_t r = r0; r < r1; ++r) {
+        const int64_t i = r * nx + col;
+        const double v = (double)i;
+        if (mode != 2) { A0[i] = v; A2[i] = v + 1.0; A4[i] = v + 2.0; }
+        if (mode == 0 || mode == 2) { nimg[i] = (uint8_t)(i & 7); flags[i] = (uint8_t)(i & 3); }
+        if (mode == 3) {
+            const int j = (int)((r - r0) & 3);
+            sb[0][j][threadIdx.x] = (uint8_t)(i & 7);
+            sb[1][j][threadIdx.x] = (uint8_t)(i & 3);
+            if (j == 3 || r == r1 - 1) {
+                __syncthreads();
+                // warp w writes row (r - j + w) of both arrays: 32 lanes x 4 bytes = 128 contiguous bytes
+                const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+                if (w <= j) {
+                    const int64_t base = (r - j + w) * nx + (int64_t)blockIdx.x * MLM_BLOCK;
+                    ((uint32_t*)(nimg + base))[l] = ((const uint32_t*)sb[0][w])[l];
+                    ((uint32_t*)(flags + base))[l] = ((const uint32_t*)sb[1][w])[l];
+                }
+                __syncthreads();
+            }
+        }
+    }
+}
+
 // FP64 FMA throughput microbenchmark: 8 independent DFMA chains per thread.
 __global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double a, double b) {
     double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
@@ -915,9 +987,9 @@ int mlm_points(mlm_context* ctx, double s, double q, double rho, double Gamma, c
     const unsigned blocks = (unsigned)((nthreads + MLM_BLOCK - 1) / MLM_BLOCK);
     cudaStream_t st = pick(ctx, stream);
     if (order == 4)
-        k_points<4><<<blocks, MLM_BLOCK, 0, st>>>(T, sf, (const double2*)zeta, n, seg, nullptr, A0, A2, A4, nimg, flags);
+        k_points<4><<<blocks, MLM_BLOCK, 0, st>>>(T, sf, (const double2*)zeta, n, seg, nullptr, nullptr, 0u, A0, A2, A4, nimg, flags);
     else
-        k_points<2><<<blocks, MLM_BLOCK, 0, st>>>(T, sf, (const double2*)zeta, n, seg, nullptr, A0, A2, A4, nimg, flags);
+        k_points<2><<<blocks, MLM_BLOCK, 0, st>>>(T, sf, (const double2*)zeta, n, seg, nullptr, nullptr, 0u, A0, A2, A4, nimg, flags);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -946,27 +1018,38 @@ int mlm_points_unordered(mlm_context* ctx, double s, double q, double rho, doubl
     uint32_t* idx = keys_out + npad;
     uint32_t* perm = idx + npad;
     void* cub_ws = perm + npad;
-    const unsigned long long init[4] = {~0ull, 0ull, ~0ull, 0ull};
+    unsigned* close = (unsigned*)(bbox + 4);
+    const unsigned long long init[5] = {~0ull, 0ull, ~0ull, 0ull, 0ull};
     cudaError_t e = cudaMemcpyAsync(bbox, init, sizeof(init), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) {
         const unsigned nb = (unsigned)((n + 255) / 256);
-        k_bbox<<<nb < 1184u ? nb : 1184u, 256, 0, st>>>((const double2*)zeta, n, bbox);
-        k_morton<<<nb, 256, 0, st>>>((const double2*)zeta, n, bbox, keys, idx);
+        k_bbox<<<nb < 592u ? nb : 592u, 256, 0, st>>>((const double2*)zeta, n, bbox);
+        k_curve_keys<<<nb, 256, 0, st>>>((const double2*)zeta, n, bbox, keys, idx);
         ctx->launches += 2;
         e = cub::DeviceRadixSort::SortPairs(cub_ws, cub_bytes, keys, keys_out, idx, perm, (int)n, 0, 32, st);
+    }
+    const int64_t npairs = (n + 7) / 8;
+    if (e == cudaSuccess) {
+        k_perm_check<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>((const double2*)zeta, perm, n, close);
+        ctx->launches++;
     }
     if (e == cudaSuccess) {
         LensTable T;
         make_table(s, q, &T);
         const SourceFactors sf = source_factors(rho, Gamma);
-        // runs of 8 sorted entries per thread: neighbours along the curve are tracked, a run start is a cold solve
-        const int seg = ctx->points_segment > 0 ? ctx->points_segment : 8;
+        // runs of 16 sorted entries per thread: neighbours along the curve are tracked, a run start is a cold solve
+        // (all lanes of a warp together); shorter runs while the list is too small to fill the GPU with 16
+        const int64_t resident = (int64_t)ctx->sm_count * 4 * MLM_BLOCK;
+        int seg = ctx->points_segment > 0 ? ctx->points_segment : (int)((n + resident - 1) / resident);
+        if (ctx->points_segment <= 0) seg = seg < 4 ? 4 : (seg > 16 ? 16 : seg);
         const int64_t nthreads = (n + seg - 1) / seg;
         const unsigned blocks = (unsigned)((nthreads + MLM_BLOCK - 1) / MLM_BLOCK);
         if (order == 4)
-            k_points<4><<<blocks, MLM_BLOCK, 0, st>>>(T, sf, (const double2*)zeta, n, seg, perm, A0, A2, A4, nimg, flags);
+            k_points<4><<<blocks, MLM_BLOCK, 0, st>>>(T, sf, (const double2*)zeta, n, seg, perm, close,
+                                                      (unsigned)(npairs * 9 / 10), A0, A2, A4, nimg, flags);
         else
-            k_points<2><<<blocks, MLM_BLOCK, 0, st>>>(T, sf, (const double2*)zeta, n, seg, perm, A0, A2, A4, nimg, flags);
+            k_points<2><<<blocks, MLM_BLOCK, 0, st>>>(T, sf, (const double2*)zeta, n, seg, perm, close,
+                                                      (unsigned)(npairs * 9 / 10), A0, A2, A4, nimg, flags);
         ctx->launches++;
         e = cudaGetLastError();
     }
@@ -1675,6 +1758,19 @@ int mlm_stats_read(mlm_context* ctx, uint64_t* out, int n, int reset) {
     (void)reset;
     return fail(ctx, MLM_ENOTSUP, "mlm_stats_read: this is the product build (counters exist in libmlmultipoles_stats.so only)");
 #endif
+}
+
+int mlm_store_probe(mlm_context* ctx, int mode, int64_t nx, int64_t nrows, int rows_per_block, double* A0, double* A2,
+                    double* A4, uint8_t* nimg, uint8_t* flags, void* stream) {
+    if (!ctx || mode < 0 || mode > 3 || nx <= 0 || nx % MLM_BLOCK || nrows <= 0 || rows_per_block <= 0 || !A0 || !A2 || !A4 ||
+        !nimg || !flags)
+        return fail(ctx, MLM_EINVAL, "mlm_store_probe: bad argument");
+    DeviceGuard g(ctx->device);
+    dim3 grid((unsigned)(nx / MLM_BLOCK), (unsigned)((nrows + rows_per_block - 1) / rows_per_block));
+    k_store_probe<<<grid, MLM_BLOCK, 0, pick(ctx, stream)>>>(mode, nx, nrows, rows_per_block, A0, A2, A4, nimg, flags);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
 }
 
 int mlm_kernel_info(mlm_context* ctx, int32_t* out, int n) {

@@ -240,14 +240,17 @@ def test_points_on_an_uneven_curved_trajectory(mb, s, q):
 
 
 def test_unordered_list_is_visited_along_a_space_filling_curve(mb):
-    """mlm_points_unordered (what magnification_points picks for a list without spatial order): Morton-sorted visiting
+    """mlm_points_unordered (what magnification_points picks for a list without spatial order): Hilbert-sorted visiting
     order with the images carried between neighbours, results at the entries' own places.  Against the plain path (one
     cold solve per entry) on the same list, and against the oracle on a sample."""
     import torch
     from oracle import cassan_oracle as oracle
     from microlensing_b200.batched import points_device
     rng = np.random.default_rng(2718)
-    for (s, q, rho, G, n, win) in ((1.0, 0.5, 1e-3, 0.5, 60000, 1.5), (0.9, 1e-3, 1e-3, 0.5, 40000, 0.6)):
+    # dense lists (neighbours along the curve ~2e-3 apart: the sorted order is used) and a sparse one (the device-side
+    # check finds the sorted order incoherent and the list is visited in its own order)
+    for (s, q, rho, G, n, win) in ((1.0, 0.5, 1e-3, 0.5, 60000, 0.3), (0.9, 1e-3, 1e-3, 0.5, 40000, 0.15),
+                                   (1.0, 0.5, 1e-3, 0.5, 20000, 2.0)):
         zeta = rng.uniform(-win, win, n) + 1j * rng.uniform(-win, win, n)
         zeta[17] = zeta[4711]                                          # duplicates are fine
         auto = mb.magnification_points(s, q, rho, G, zeta)            # >= 8192 entries without order -> sorted path
