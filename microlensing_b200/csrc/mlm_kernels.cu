@@ -93,16 +93,27 @@ k_points(const __grid_constant__ LensTable T, const SourceFactors sf, const doub
     cd* const sz = &s_roots[0][0][threadIdx.x];
     cd* const szp = &s_roots[1][0][threadIdx.x];
     const int64_t i0 = ((int64_t)blockIdx.x * MLM_BLOCK + threadIdx.x) * seg;
-    if (i0 >= n) return;
     const int64_t i1 = (i0 + seg < n) ? i0 + seg : n;
     TrackState st;
     st.hist = 0; st.nimg = 0; st.extra = 0;
     cd zprev = mk(0.0, 0.0), dprev = mk(0.0, 0.0);
-    for (int64_t iv = i0; iv < i1; ++iv) {
-        const int64_t i = perm ? (int64_t)__ldg(perm + iv) : iv;
+    // every lane runs `seg` iterations (entries past the end are skipped) and the warp RECONVERGES at the two
+    // __syncwarp() of an iteration: without them lanes whose cold solve took fewer Laguerre iterations run ahead into
+    // the next entries on their own and the warp ends up executing the loop body several times over (measured on
+    // an unordered list: 12 of 32 lanes active)
+    for (int j = 0; j < seg; ++j) {
+        const int64_t iv = i0 + j;
+        const bool act = iv < i1;
+        PointResult r;
+        r.flags = 0;
+        int64_t i = 0;
+        cd zt = mk(0.0, 0.0), d = mk(0.0, 0.0);
+        __syncwarp();
+        if (act) {
+        i = perm ? (int64_t)__ldg(perm + iv) : iv;
         const double2 zz = __ldg(zeta + i);
-        const cd zt = mk(zz.x, zz.y);
-        const cd d = zt - zprev;
+        zt = mk(zz.x, zz.y);
+        d = zt - zprev;
         const double d2 = norm2(d);
         double ratio = 1.0;
         // jump of more than 0.02 Einstein radii (or NaN): start afresh.  Tracking across larger steps often
@@ -114,14 +125,16 @@ k_points(const __grid_constant__ LensTable T, const SourceFactors sf, const doub
             ratio = re_mulc(d, dprev) * rcp(norm2(dprev));
             if (!(ratio > 0.0 && ratio < 4.0)) st.hist = 1;
         }
-        PointResult r;
-        r.flags = 0;
         MLM_COUNT(positions);
         advance_images(T, zt, sz, szp, nullptr, MLM_BLOCK, st, r.flags, ratio);
-        sum_images<ORDER>(T, sf, sz, MLM_BLOCK, st.nimg, r);
-        store_result(r, i, A0, A2, A4, nimg, flags);
-        zprev = zt;
-        dprev = d;
+        }
+        __syncwarp();
+        if (act) {
+            sum_images<ORDER>(T, sf, sz, MLM_BLOCK, st.nimg, r);
+            store_result(r, i, A0, A2, A4, nimg, flags);
+            zprev = zt;
+            dprev = d;
+        }
     }
 }
 
@@ -250,7 +263,6 @@ k_anchor(const __grid_constant__ LensTable T, double x0, double y0, double dx, d
     cd* const szp = &s_roots[1][0][threadIdx.x];
     cd* const szpp = &s_roots[2][0][threadIdx.x];
     const int64_t c0 = ((int64_t)blockIdx.x * MLM_BLOCK + threadIdx.x) * aseg;
-    if (c0 >= nx) return;
     const int64_t c1 = (c0 + aseg < nx) ? c0 + aseg : nx;
     for (int64_t ii = blockIdx.y; ii < i_count; ii += gridDim.y) {
         const int64_t k = deal_strip(deal, deal.t0 + ii);
@@ -258,7 +270,10 @@ k_anchor(const __grid_constant__ LensTable T, double x0, double y0, double dx, d
         const double y = __dadd_rn(y0, __dmul_rn((double)ra + 0.5, dy));
         TrackState st;
         st.hist = 0; st.nimg = 0; st.extra = 0;
-        for (int64_t c = c0; c < c1; ++c) {
+        for (int j0 = 0; j0 < aseg; ++j0) {
+            const int64_t c = c0 + j0;
+            __syncwarp();                                // whole warps take every column step together
+            if (c >= c1) continue;
             const double x = __dadd_rn(__dadd_rn(x0, __dmul_rn((double)c + 0.5, dx)), -shift);
             unsigned fl = 0;
             MLM_COUNT(anchor_positions);
@@ -279,8 +294,12 @@ __global__ void __launch_bounds__(MLM_BLOCK, MLM_MAP_MINBLOCKS)
 k_map(const __grid_constant__ LensTable T, const SourceFactors sf, double x0, double y0, double dx, double dy,
       double shift, int64_t nx, int64_t row0, int64_t nrows, int strip, const __grid_constant__ Deal deal,
       int64_t i_count, int64_t i_axis, const double2* __restrict__ aroots, const uint16_t* __restrict__ ameta,
-      double* __restrict__ A0,
+      int u8rows, double* __restrict__ A0,
       double* __restrict__ A2, double* __restrict__ A4, uint8_t* __restrict__ nimg, uint8_t* __restrict__ flags) {
+    // u8rows (outputs in ANOTHER GPU's memory): the one-byte arrays are staged in shared memory for four rows and
+    // written 128 contiguous bytes per row by one warp instead of 32 bytes per warp and row -- 32-byte stores are what
+    // holds the kernel's peer stores at ~670 GB/s over NVLink when 128-byte ones reach ~720 (tools/peer_store_probe.py)
+    __shared__ uint8_t s_u8[2][4][MLM_BLOCK];
     // root store of this thread: current and previous roots, [k][thread] so that a warp touches
     // 512 contiguous bytes per k (conflict-free); keeps 20 doubles out of the register file
     __shared__ cd s_roots[3][5][MLM_BLOCK];
@@ -288,7 +307,7 @@ k_map(const __grid_constant__ LensTable T, const SourceFactors sf, double x0, do
     cd* const szp = &s_roots[1][0][threadIdx.x];
     cd* const szpp = &s_roots[2][0][threadIdx.x];
     const int64_t col = (int64_t)blockIdx.x * MLM_BLOCK + threadIdx.x;
-    if (col >= nx) return;
+    const bool act = col < nx;                         // lanes past the last column idle but keep the warp whole
     // x = x0 + (col + 0.5) dx with two roundings (no FMA), so that host code can reproduce
     // the coordinates bit for bit with the same expression.
     const double x = __dadd_rn(__dadd_rn(x0, __dmul_rn((double)col + 0.5, dx)), -shift);
@@ -309,7 +328,7 @@ k_map(const __grid_constant__ LensTable T, const SourceFactors sf, double x0, do
         st.hist = 0; st.nimg = 0; st.extra = 0;
         // the strip starts from its anchor (roots found by k_anchor at exactly this pixel) when there is one
         unsigned anchor = 0;
-        if (ameta != nullptr) {
+        if (ameta != nullptr && act) {
             anchor = __ldg(ameta + ii * nx + col);
             if (anchor & MLM_ANCHOR_VALID) {
 #pragma unroll
@@ -325,11 +344,32 @@ k_map(const __grid_constant__ LensTable T, const SourceFactors sf, double x0, do
             const cd zeta = mk(x, y);
             PointResult res;
             res.flags = 0;
-            MLM_COUNT(positions);
-            if (r == ra && (anchor & MLM_ANCHOR_VALID)) res.flags = anchor & 0xffu;     // the anchor IS this pixel's solution
-            else advance_images(T, zeta, sz, szp, szpp, MLM_BLOCK, st, res.flags);
-            sum_images<ORDER>(T, sf, sz, MLM_BLOCK, st.nimg, res);
-            store_result(res, (r - row0) * nx + col, A0, A2, A4, nimg, flags);
+            __syncwarp();                                // the lanes of a warp take every row together
+            if (act) {
+                MLM_COUNT(positions);
+                if (r == ra && (anchor & MLM_ANCHOR_VALID)) res.flags = anchor & 0xffu;     // the anchor IS this pixel's solution
+                else advance_images(T, zeta, sz, szp, szpp, MLM_BLOCK, st, res.flags);
+            }
+            __syncwarp();
+            if (act) {
+                sum_images<ORDER>(T, sf, sz, MLM_BLOCK, st.nimg, res);
+                store_result(res, (r - row0) * nx + col, A0, A2, A4, u8rows ? nullptr : nimg, u8rows ? nullptr : flags);
+            }
+            if (u8rows) {                                // block-uniform
+                const int jr = (int)((r - ra) & 3);
+                s_u8[0][jr][threadIdx.x] = (uint8_t)res.nimg;
+                s_u8[1][jr][threadIdx.x] = (uint8_t)res.flags;
+                if (jr == 3 || r == rb - 1) {
+                    __syncthreads();
+                    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+                    if (w <= jr) {                       // warp w writes row r - jr + w of this block's 128 columns
+                        const int64_t base = (r - jr + w - row0) * nx + (int64_t)blockIdx.x * MLM_BLOCK;
+                        if (nimg) ((uint32_t*)(nimg + base))[l] = ((const uint32_t*)s_u8[0][w])[l];
+                        if (flags) ((uint32_t*)(flags + base))[l] = ((const uint32_t*)s_u8[1][w])[l];
+                    }
+                    __syncthreads();
+                }
+            }
         }
     }
 }
@@ -413,18 +453,23 @@ k_models(const double* __restrict__ s, const double* __restrict__ q, const doubl
         if (threadIdx.x < G && mb * G + threadIdx.x < M) stage_model(&slots[threadIdx.x], s, q, rho, Gamma, alpha, mb * G + threadIdx.x);
         __syncthreads();
         const int64_t m = mb * G + g;
-        if (m >= M) continue;
-        const ModelSlot& ms = slots[g];
-        const double u = u0[m];
+        const bool have_model = m < M;
+        const ModelSlot& ms = slots[have_model ? g : 0];
+        const double u = have_model ? u0[m] : 0.0;
         const double ur1 = __dmul_rn(u, ms.sa), ur0 = __dmul_rn(u, ms.ca);
-        const double t0m = ep.t0 ? ep.t0[m] : 0.0, tEm = ep.tE ? ep.tE[m] : 1.0;
-        for (int64_t sg = (int64_t)blockIdx.x * P + lane; sg < nseg; sg += (int64_t)gridDim.x * P) {
+        const double t0m = (have_model && ep.t0) ? ep.t0[m] : 0.0, tEm = (have_model && ep.tE) ? ep.tE[m] : 1.0;
+        // block-uniform trip counts (idle lanes skip the bodies) so that the warps can reconverge at every epoch
+        for (int64_t sbase = (int64_t)blockIdx.x * P; sbase < nseg; sbase += (int64_t)gridDim.x * P) {
+            const int64_t sg = sbase + lane;
             const int64_t t0 = sg * seg;
-            const int64_t t1 = (t0 + seg < Tn) ? t0 + seg : Tn;
+            const int64_t t1 = (!have_model || sg >= nseg) ? t0 : ((t0 + seg < Tn) ? t0 + seg : Tn);
             TrackState st;
             st.hist = 0; st.nimg = 0; st.extra = 0;
             double tau_prev = 0.0, dt_prev = 1.0;
-            for (int64_t t = t0; t < t1; ++t) {
+            for (int jt = 0; jt < seg; ++jt) {
+                const int64_t t = t0 + jt;
+                __syncwarp();
+                if (t >= t1) continue;
                 // compiler barrier: the table is re-read from shared memory where it is used instead of
                 // being hoisted out of the loop into ~40 live registers
                 asm volatile("" ::: "memory");
@@ -473,18 +518,23 @@ k_models_chi2(const double* __restrict__ s, const double* __restrict__ q, const 
         __syncthreads();
         const int64_t m = mb * G + g;
         double a_w = 0.0, a_wa = 0.0, a_waa = 0.0, a_wf = 0.0, a_waf = 0.0, a_wff = 0.0, a_n5 = 0.0, a_nf = 0.0;
-        if (m < M) {
-            const ModelSlot& ms = slots[g];
-            const double u = u0[m];
+        {
+            const bool have_model = m < M;
+            const ModelSlot& ms = slots[have_model ? g : 0];
+            const double u = have_model ? u0[m] : 0.0;
             const double ur1 = __dmul_rn(u, ms.sa), ur0 = __dmul_rn(u, ms.ca);
-            const double t0m = ep.t0 ? ep.t0[m] : 0.0, tEm = ep.tE ? ep.tE[m] : 1.0;
-            for (int64_t sg = lane; sg < nseg; sg += P) {
+            const double t0m = (have_model && ep.t0) ? ep.t0[m] : 0.0, tEm = (have_model && ep.tE) ? ep.tE[m] : 1.0;
+            for (int64_t sbase = 0; sbase < nseg; sbase += P) {      // block-uniform trip counts, see k_models
+                const int64_t sg = sbase + lane;
                 const int64_t t0 = sg * seg;
-                const int64_t t1 = (t0 + seg < Tn) ? t0 + seg : Tn;
+                const int64_t t1 = (!have_model || sg >= nseg) ? t0 : ((t0 + seg < Tn) ? t0 + seg : Tn);
                 TrackState st;
                 st.hist = 0; st.nimg = 0; st.extra = 0;
                 double tau_prev = 0.0, dt_prev = 1.0;
-                for (int64_t t = t0; t < t1; ++t) {
+                for (int jt = 0; jt < seg; ++jt) {
+                    const int64_t t = t0 + jt;
+                    __syncwarp();
+                    if (t >= t1) continue;
                     asm volatile("" ::: "memory");
                     const double tau = epoch_tau(ep, t, t0m, tEm);
                     const double ratio = epoch_ratio(ep, tau, tau_prev, dt_prev, st);
@@ -701,6 +751,7 @@ struct mlm_context {
     // caller's stream and touch no context state.
     std::recursive_mutex mu;
     int anchor_segment = 16;                           // columns per thread of k_anchor (MLM_MAP_ANCHOR; 0: no anchors, cold strip starts)
+    int u8rows_env = -1;                               // MLM_MAP_U8ROWS = 0/1 forces the row-wise one-byte stores off/on (experiments)
     int points_segment = 0;                            // consecutive list entries per thread of k_points (0: from n; MLM_POINTS_SEGMENT)
     int models_segment = 0;                            // epochs per warm-start segment of k_models (0: from T; MLM_SEGMENT)
 };
@@ -797,6 +848,7 @@ int mlm_create(int device, mlm_context** out) {
         const int v = atoi(e2);
         if (v >= 1 && v <= 4096) ctx->map_strip_env = v;
     }
+    if (const char* e6 = getenv("MLM_MAP_U8ROWS")) ctx->u8rows_env = atoi(e6) ? 1 : 0;
     if (const char* e5 = getenv("MLM_MAP_ANCHOR")) {
         const int v = atoi(e5);
         if (v >= 0 && v <= 4096) ctx->anchor_segment = v;
@@ -1122,12 +1174,23 @@ int mlm_map_deal(mlm_context* ctx, double s, double q, double rho, double Gamma,
             ws = nullptr;
         }
     }
+    // one-byte outputs that live in another GPU's memory are written a 128-byte row segment at a time
+    int u8rows = 0;
+    if ((nimg || flags) && nx % MLM_BLOCK == 0) {
+        cudaPointerAttributes pa;
+        const void* p8 = nimg ? (const void*)nimg : (const void*)flags;
+        if (cudaPointerGetAttributes(&pa, p8) == cudaSuccess && pa.type == cudaMemoryTypeDevice && pa.device != ctx->device &&
+            (((uintptr_t)nimg | (uintptr_t)flags) & 3u) == 0)
+            u8rows = 1;
+        cudaGetLastError();
+        if (ctx->u8rows_env >= 0) u8rows = ctx->u8rows_env && (((uintptr_t)nimg | (uintptr_t)flags) & 3u) == 0;
+    }
     if (order == 4)
         k_map<4><<<grid, MLM_BLOCK, 0, st>>>(T, sf, x0, y0, dx, dy, shift, nx, row0, nrows, strip, deal, i_count, i_axis,
-                                              aroots, ameta, A0, A2, A4, nimg, flags);
+                                              aroots, ameta, u8rows, A0, A2, A4, nimg, flags);
     else
         k_map<2><<<grid, MLM_BLOCK, 0, st>>>(T, sf, x0, y0, dx, dy, shift, nx, row0, nrows, strip, deal, i_count, i_axis,
-                                              aroots, ameta, A0, A2, A4, nimg, flags);
+                                              aroots, ameta, u8rows, A0, A2, A4, nimg, flags);
     ctx->launches++;
     cudaError_t le = cudaGetLastError();
     if (ws) cudaFreeAsync(ws, st);
