@@ -137,6 +137,51 @@ MLM_HD cd csqrt_(cd a) {
 }
 
 // ---------------------------------------------------------------------------------------
+// single-precision complex helpers: only for the WATCH of the two non-physical roots on the tracking path
+// (advance_images), a yes/no question with a threshold of 0.1 -- it runs on the FP32 pipe, which is otherwise
+// idle in these kernels, instead of the FP64 pipe that bounds them.  MUFU seeds without refinement (1-2 ulp).
+// ---------------------------------------------------------------------------------------
+struct cf {
+    float x, y;
+};
+MLM_HD cf mkf(float x, float y) { cf r; r.x = x; r.y = y; return r; }
+MLM_HD cf tof(cd a) { return mkf((float)a.x, (float)a.y); }
+MLM_HD float rcpf_(float a) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(a));
+    return r;
+#else
+    return 1.0f / a;
+#endif
+}
+MLM_HD float rsqrtf_(float a) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rsqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(a));
+    return r;
+#else
+    return 1.0f / sqrtf(a);
+#endif
+}
+MLM_HD float norm2f(cf a) { return fmaf(a.x, a.x, a.y * a.y); }
+MLM_HD cf cmulf(cf a, cf b) { return mkf(fmaf(a.x, b.x, -(a.y * b.y)), fmaf(a.x, b.y, a.y * b.x)); }
+MLM_HD cf crcpf(cf a) {
+    const float r = rcpf_(norm2f(a));
+    return mkf(a.x * r, -(a.y * r));
+}
+MLM_HD cf csqrtf_(cf a) {                             // principal square root, same scheme as csqrt_
+    const float n2 = norm2f(a);
+    if (!(n2 > 0.0f)) return mkf(0.0f, 0.0f);
+    const float r = n2 * rsqrtf_(n2);
+    const float h = 0.5f * (r + fabsf(a.x));
+    const float rs = rsqrtf_(h);
+    const float t = h * rs;
+    const float u = 0.5f * a.y * rs;
+    return (a.x >= 0.0f) ? mkf(t, u) : mkf(fabsf(u), (a.y >= 0.0f) ? t : -t);
+}
+
+// ---------------------------------------------------------------------------------------
 // per-(s,q) table (kernel parameter -> constant bank; built on the host by mlm_make_table)
 // ---------------------------------------------------------------------------------------
 struct LensTable {
@@ -149,6 +194,7 @@ struct LensTable {
     double k00;
     double alpha[7];                                  // W_k = alpha_k z^-k + beta_k (z+s)^-k, k=1..6
     double beta[7];
+    float s_f, alpha1_f, beta1_f, pad_f;              // s, alpha[1], beta[1] in single precision (watch_nonphysical)
 };
 
 MLM_HDI void make_table(double s, double q, LensTable* t) {
@@ -168,6 +214,7 @@ MLM_HDI void make_table(double s, double q, LensTable* t) {
         t->alpha[k] = f / m;
         t->beta[k] = f * q / m;
     }
+    t->s_f = (float)s; t->alpha1_f = (float)t->alpha[1]; t->beta1_f = (float)t->beta[1]; t->pad_f = 0.0f;
 }
 
 // (a) coefficients c[k] of z^k, k = 0..5        (multipoles.py:159-164, A.2 of SURVEY.md)
@@ -511,13 +558,14 @@ struct PointResult {
 // =======================================================================================
 
 // One Newton iteration on f(z) = z - zeta - conj(W1(z)):  dz = -(f + conj(W2) conj(f)) / (1 - |W2|^2).
-// d2 = squared distance of z to the nearer lens (the scale on which the images live).
-MLM_HD cd lens_newton(const LensTable& T, cd zeta, cd z, double& dz2, double& d2, double& z2) {
+// z2, zs2 = squared distances of z to the two lenses (their minimum is the scale on which the images live).
+MLM_HD cd lens_newton(const LensTable& T, cd zeta, cd z, double& dz2, double& z2, double& zs2) {
     const cd zs = mk(z.x + T.s, z.y);
     z2 = norm2(z);
-    const double zs2 = norm2(zs);
-    d2 = fmin(z2, zs2);
-    const double i1 = rcp(z2), i2 = rcp(zs2);
+    zs2 = norm2(zs);
+    // one reciprocal for both: 1/|z|^2 = |z+s|^2 / (|z|^2 |z+s|^2)
+    const double i12 = rcp(z2 * zs2);
+    const double i1 = i12 * zs2, i2 = i12 * z2;
     const cd r1 = mk(z.x * i1, -(z.y * i1)), r2 = mk(zs.x * i2, -(zs.y * i2));
     const cd W1 = rfma(T.alpha[1], r1, scale(T.beta[1], r2));
     const cd f = z - zeta - conj(W1);
@@ -611,11 +659,11 @@ MLM_HD int classify_roots(const LensTable& T, cd zeta, cd* sz, int stride, unsig
                 double lim = 1e300;
 #pragma unroll 1
                 for (int it = 0; it < 8; ++it) {
-                    double dz2, d2, z2;
-                    const cd z1 = lens_newton(T, zeta, zn, dz2, d2, z2);
+                    double dz2, z2, zs2;
+                    const cd z1 = lens_newton(T, zeta, zn, dz2, z2, zs2);
                     if (!(dz2 < lim)) break;
                     zn = z1;
-                    if (dz2 <= fmax(1e-24 * d2, 3.2e-30 * z2)) { conv = true; break; }
+                    if (dz2 <= fmax(1e-24 * fmin(z2, zs2), 3.2e-30 * z2)) { conv = true; break; }
                     lim = 0.25 * dz2;
                 }
                 if (!conv) continue;
@@ -701,6 +749,32 @@ MLM_HD double lens_residual2(const LensTable& T, cd zeta, cd z) {
     return norm2(z - zeta - conj(W1));
 }
 
+// WATCH of the two roots of the quintic that are not images (three-image state): is the lens-equation residual of
+// one of them below ~0.1, i.e. are they about to turn physical?  They follow from the three images by Vieta (sum S,
+// product P -> a quadratic).  The answer decides nothing but whether the position is looked at in double precision,
+// and the threshold (1.5e-2 on the squared residual, against 1e-2 of the double-precision test behind it) is twelve
+// orders of magnitude above the single-precision rounding of the residual, so this runs in FP32 -- on the pipe that
+// these FP64-bound kernels leave idle.  Overflow, underflow or NaN anywhere answer "near" (conservative).
+MLM_HD bool nonphysical_pair_near(const LensTable& T, cd zeta, cd S, cd c0, cd ic5, cd z0, cd z1, cd z2) {
+    const cf Sf = tof(S), ztf = tof(zeta);
+    const cf Pf = cmulf(cmulf(tof(c0), tof(ic5)), crcpf(cmulf(cmulf(tof(z0), tof(z1)), tof(z2))));   // = -P
+    cf sq = csqrtf_(mkf(fmaf(4.0f, Pf.x, fmaf(Sf.x, Sf.x, -(Sf.y * Sf.y))), fmaf(4.0f, Pf.y, 2.0f * (Sf.x * Sf.y))));
+    if (fmaf(Sf.x, sq.x, Sf.y * sq.y) < 0.0f) sq = mkf(-sq.x, -sq.y);
+    const cf r4 = mkf(0.5f * (Sf.x + sq.x), 0.5f * (Sf.y + sq.y));
+    const cf r5 = cmulf(mkf(-Pf.x, -Pf.y), crcpf(r4));
+    float res[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const cf z = j ? r5 : r4;
+        const cf i1 = crcpf(z), i2 = crcpf(mkf(z.x + T.s_f, z.y));
+        // f = z - zeta - conj(W1)
+        const float fx = z.x - ztf.x - fmaf(T.alpha1_f, i1.x, T.beta1_f * i2.x);
+        const float fy = z.y - ztf.y + fmaf(T.alpha1_f, i1.y, T.beta1_f * i2.y);
+        res[j] = fmaf(fx, fx, fy * fy);
+    }
+    return !(res[0] >= 1.5e-2f && res[1] >= 1.5e-2f && res[0] < 1e30f && res[1] < 1e30f);
+}
+
 // Newton on the quintic from zk until newton_stop (at most 6 steps); false: not converged
 MLM_HD bool quintic_newton(const cd c[6], double s, cd& zk) {
     double prev = 1e300;
@@ -736,12 +810,13 @@ MLM_HD void advance_images(const LensTable& T, cd zeta, cd* sz, cd* szp, cd* szp
             double lim = 1e300;
 #pragma unroll 1
             for (int it = 0; it < 4; ++it) {
-                double dz2, d2, z2;
-                const cd zn = lens_newton(T, zeta, zk, dz2, d2, z2);
+                double dz2, z2, zs2;
+                const cd zn = lens_newton(T, zeta, zk, dz2, z2, zs2);
                 MLM_COUNT(lens_evals);
                 if (!(dz2 < lim)) break;
                 zk = zn;
-                if (dz2 <= fmax(1e-14 * d2, 3.2e-30 * z2)) { conv = true; break; }
+                // dz2 <= max(1e-14 min(z2, zs2), 3.2e-30 z2), written as comparisons (no min/max selects)
+                if (dz2 <= 1e-14 * z2 && (dz2 <= 1e-14 * zs2 || dz2 <= 3.2e-30 * z2)) { conv = true; break; }
                 lim = 1e-2 * dz2;
             }
             ok = ok && conv;
@@ -756,29 +831,34 @@ MLM_HD void advance_images(const LensTable& T, cd zeta, cd* sz, cd* szp, cd* szp
             // three DISTINCT images?  (two tracks that collapsed onto one image differ by rounding only)
             const double tol = 1e-14 * mag;
             ok = ok && norm2(z0 - z1) > tol && norm2(z0 - z2) > tol && norm2(z1 - z2) > tol;
-            // r4 + r5 = S, r4 r5 = P  ->  z^2 - S z + P = 0 (stable form: the larger root first)
+            // r4 + r5 = S, r4 r5 = P  ->  z^2 - S z + P = 0.  S in double (a difference of sums of roots: it cancels
+            // for a distant source); everything after it is the WATCH, in single precision
             const cd ic5 = crcp(c5);
             const cd S = -(cfma(c4, ic5, sum));
-            const cd P = -(cmul(cmul(c0, ic5), crcp(cmul(cmul(z0, z1), z2))));
-            cd sq = csqrt_(rfma(-4.0, P, csq(S)));
-            if (re_mulc(S, sq) < 0.0) sq = -sq;
-            cd r4 = scale(0.5, S + sq);
-            cd r5 = cmul(P, crcp(r4));
             //@phase track_nonphys_check
             MLM_COUNT(nonphys_checks);
             MLM_COUNT(nonphys_checks);
-            if (lens_residual2(T, zeta, r4) < 1e-2 || lens_residual2(T, zeta, r5) < 1e-2) {
+            if (nonphysical_pair_near(T, zeta, S, c0, ic5, z0, z1, z2)) {
                 //@phase track_polish
-                // they may have turned physical (caustic crossing): classify them like freshly solved roots, i.e.
-                // at the accuracy of a polished polynomial root (the quadratic loses digits where the two merge)
-                need_classify = true;
-                cd c[6];
-                lens_polynomial(T, zeta, c);
-                ok = quintic_newton(c, T.s, r4) && ok;
-                ok = quintic_newton(c, T.s, r5) && ok;
+                MLM_COUNT(watch_near);
+                // the same question in double, then: they may have turned physical (caustic crossing): classify them
+                // like freshly solved roots, i.e. at the accuracy of a polished polynomial root (the quadratic loses
+                // digits where the two merge)
+                const cd P = -(cmul(cmul(c0, ic5), crcp(cmul(cmul(z0, z1), z2))));
+                cd sq = csqrt_(rfma(-4.0, P, csq(S)));
+                if (re_mulc(S, sq) < 0.0) sq = -sq;
+                cd r4 = scale(0.5, S + sq);               // stable form: the larger root first
+                cd r5 = cmul(P, crcp(r4));
+                if (lens_residual2(T, zeta, r4) < 1e-2 || lens_residual2(T, zeta, r5) < 1e-2) {
+                    need_classify = true;
+                    cd c[6];
+                    lens_polynomial(T, zeta, c);
+                    ok = quintic_newton(c, T.s, r4) && ok;
+                    ok = quintic_newton(c, T.s, r5) && ok;
+                }
+                sz[3 * stride] = r4;
+                sz[4 * stride] = r5;
             }
-            sz[3 * stride] = r4;
-            sz[4 * stride] = r5;
         } else {
             //@phase track_general
             if (nimg < 5) {
@@ -845,7 +925,11 @@ MLM_HD void sum_images(const LensTable& T, const SourceFactors sf, const cd* sz,
         MLM_COUNT(images);
         const cd zk = sz[k * stride];
         const cd zs = mk(zk.x + T.s, zk.y);
-        const cd r1 = crcp(zk), r2 = crcp(zs);
+        // 1/z and 1/(z+s) from one reciprocal
+        const double n1 = norm2(zk), n2 = norm2(zs);
+        const double i12 = rcp(n1 * n2);
+        const double i1 = i12 * n2, i2 = i12 * n1;
+        const cd r1 = mk(zk.x * i1, -(zk.y * i1)), r2 = mk(zs.x * i2, -(zs.y * i2));
         const cd a2 = csq(r1), b2 = csq(r2);
         const cd a3 = cmul(a2, r1), b3 = cmul(b2, r2);
         const cd a4 = csq(a2), b4 = csq(b2);

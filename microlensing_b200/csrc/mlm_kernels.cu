@@ -26,7 +26,7 @@
 // count what a kernel executes): every MLM_COUNT(event) of mlm_core.cuh adds the number of active lanes to
 // g_mlm_cnt[0][event] and 1 to g_mlm_cnt[1][event] (one atomic pair per warp-level event).
 #define MLM_CNT_NAMES(X) X(positions) X(laguerre_evals) X(newton_evals) X(lens_evals) X(track_fallbacks) X(cold_solves) \
-    X(classify_calls) X(classify_newton) X(nonphys_checks) X(images) X(quadratics) X(anchor_positions)
+    X(classify_calls) X(classify_newton) X(nonphys_checks) X(images) X(quadratics) X(anchor_positions) X(watch_near)
 enum {
 #define X(n) MLM_CNT_##n,
     MLM_CNT_NAMES(X)

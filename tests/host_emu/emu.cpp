@@ -3,7 +3,7 @@
 // recursion) against the oracle without a GPU.  Never loaded by microlensing_b200.
 #ifdef MLM_STATS
 static long g_cnt_laguerre_evals = 0, g_cnt_newton_evals = 0, g_cnt_track_fallbacks = 0, g_cnt_lens_evals = 0;
-static long g_cnt_cold_solves = 0, g_cnt_classify_calls = 0, g_cnt_classify_newton = 0, g_cnt_nonphys_checks = 0, g_cnt_images = 0, g_cnt_quadratics = 0, g_cnt_anchor_positions = 0;
+static long g_cnt_cold_solves = 0, g_cnt_classify_calls = 0, g_cnt_classify_newton = 0, g_cnt_nonphys_checks = 0, g_cnt_images = 0, g_cnt_quadratics = 0, g_cnt_anchor_positions = 0, g_cnt_watch_near = 0;
 #define MLM_COUNT(name) (++g_cnt_##name)
 #endif
 #include "../../microlensing_b200/csrc/mlm_core.cuh"

@@ -24,7 +24,7 @@ import tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "microlensing_b200", "csrc")
 PHASE_FUNCS = {"lens_polynomial": "polynomial", "solve_roots": "cold_solve", "classify_roots": "classify",
-               "lens_newton": "lens_newton", "image_terms_from_W": "image_terms", "sum_images": "image_sums",
+               "lens_newton": "lens_newton", "nonphysical_pair_near": "watch_fp32", "image_terms_from_W": "image_terms", "sum_images": "image_sums",
                "advance_images": "track_other", "store_result": "store", "epoch_tau": "coords", "epoch_ratio": "coords"}
 FP64_OPS = ("DFMA", "DMUL", "DADD", "DSETP", "DMNMX", "DFMA.RN", "DFMA.RM", "DFMA.RP")
 
@@ -193,12 +193,12 @@ def main():
     order = sorted(table, key=lambda p: -table[p]["fp64_thread"])
     md = [f"Per-phase executed instructions of `{kre}` per source position ({npos:.0f} positions; `{os.path.basename(rep)}`;",
           "thread-level, predicated-on; FP64 = DFMA+DMUL+DADD+DSETP+DMNMX; lanes = FP64 thread / (32 x FP64 warp instructions))", "",
-          "| phase | static SASS | all thread instr | FP64 | DFMA | DMUL | DADD | share of FP64 | active lanes |", "|---|---|---|---|---|---|---|---|---|"]
+          "| phase | static SASS | all thread instr | FP64 | DFMA | DMUL | DADD | share of FP64 | active lanes | warp instr x32 (all) | warp instr x32 (FP64) |", "|---|---|---|---|---|---|---|---|---|---|---|"]
     for ph in order + ["TOTAL"]:
         t = tot if ph == "TOTAL" else table[ph]
         md.append(f"| {ph} | {t['static']} | {t['thread_inst'] / npos:.1f} | {t['fp64_thread'] / npos:.1f} | {t['dfma'] / npos:.1f} | "
                   f"{t['dmul'] / npos:.1f} | {t['dadd'] / npos:.1f} | {100 * t['fp64_thread'] / max(tot['fp64_thread'], 1):.1f} % | "
-                  f"{t['fp64_thread'] / max(t['fp64_warp'], 1):.1f} |")
+                  f"{t['fp64_thread'] / max(t['fp64_warp'], 1):.1f} | {32 * t['warp_inst'] / npos:.1f} | {32 * t['fp64_warp'] / npos:.1f} |")
     with open(out + ".md", "w") as f:
         f.write("\n".join(md) + "\n")
     print("\n".join(md))
