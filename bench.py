@@ -261,6 +261,8 @@ def parity_block(got_n, got_A, got_flags, ref, par, zeta, what, max_adjudicate=9
            "of_which_flagged_extra": rep.get("nimg_mismatch_flagged_extra"),
            "of_which_reference_ambiguous": rep.get("nimg_mismatch_ref_ambiguous"),
            "nimg_mismatch_unaccounted": rep.get("nimg_mismatch_unaccounted"),
+           "disputes_outside_rule3_mask": rep["unmasked_disputes"],
+           "disputes_outside_rule3_mask_rate": rep["unmasked_disputes"] / max(rep["n"], 1),
            "rel_gt_1e-9": rep["rel_gt_tol"], "rel_gt_1e-9_unflagged_unmasked": rep.get("rel_gt_tol_unflagged_unmasked"),
            "masked_by_reference_side_rule3": rep["masked"], "flagged_any": int((fl != 0).sum()),
            "flagged_extra": rep.get("flagged_extra"), "max_rel_undisputed": rep["max_rel_clean"],

@@ -382,6 +382,12 @@ k_map(const __grid_constant__ LensTable T, const SourceFactors sf, double x0, do
 // models' tables sit in shared memory.  seg is an argument of the call (like the strip length of a map): the bits
 // of a light curve depend on it, not on how the grid is sharded over ranks.
 #define MLM_MODELS_BLOCK 64
+#ifndef MLM_MODELS_MINBLOCKS
+#define MLM_MODELS_MINBLOCKS 8      /* k_models on a uniform grid: 128 registers -> 8 blocks (16 warps) per SM, no spill */
+#endif
+#ifndef MLM_CHI2_MINBLOCKS
+#define MLM_CHI2_MINBLOCKS 6        /* observation times (four doubles more per thread) and k_models_chi2 (six accumulators more) */
+#endif
 #define MLM_MODELS_GMAX 16                            /* models per block: P >= 4 threads per model */
 
 // Epochs of the light curves of a model grid: tau_t = tau0 + t dtau (uniform grid, times == NULL) or
@@ -433,11 +439,11 @@ __device__ __forceinline__ void stage_model(ModelSlot* slot, const double* s, co
     slot->ca = ca; slot->sa = sa; slot->shift = sm * qm / (1.0 + qm);
 }
 
-template <int ORDER>
-__global__ void __launch_bounds__(MLM_MODELS_BLOCK, 6)
+template <int ORDER, bool TIMES>
+__global__ void __launch_bounds__(MLM_MODELS_BLOCK, TIMES ? MLM_CHI2_MINBLOCKS : MLM_MODELS_MINBLOCKS)
 k_models(const double* __restrict__ s, const double* __restrict__ q, const double* __restrict__ rho,
          const double* __restrict__ Gamma, const double* __restrict__ u0, const double* __restrict__ alpha,
-         int64_t M, const Epochs ep, int64_t Tn, int seg, int P, double* __restrict__ A0,
+         int64_t M, const __grid_constant__ Epochs ep, int64_t Tn, int seg, int P, double* __restrict__ A0,
          double* __restrict__ A2, double* __restrict__ A4, uint8_t* __restrict__ nimg, uint8_t* __restrict__ flags) {
     __shared__ ModelSlot slots[MLM_MODELS_GMAX];
     __shared__ cd s_roots[3][5][MLM_MODELS_BLOCK];
@@ -457,7 +463,7 @@ k_models(const double* __restrict__ s, const double* __restrict__ q, const doubl
         const ModelSlot& ms = slots[have_model ? g : 0];
         const double u = have_model ? u0[m] : 0.0;
         const double ur1 = __dmul_rn(u, ms.sa), ur0 = __dmul_rn(u, ms.ca);
-        const double t0m = (have_model && ep.t0) ? ep.t0[m] : 0.0, tEm = (have_model && ep.tE) ? ep.tE[m] : 1.0;
+        const double t0m = (TIMES && have_model && ep.t0) ? ep.t0[m] : 0.0, tEm = (TIMES && have_model && ep.tE) ? ep.tE[m] : 1.0;
         // block-uniform trip counts (idle lanes skip the bodies) so that the warps can reconverge at every epoch
         for (int64_t sbase = (int64_t)blockIdx.x * P; sbase < nseg; sbase += (int64_t)gridDim.x * P) {
             const int64_t sg = sbase + lane;
@@ -468,21 +474,24 @@ k_models(const double* __restrict__ s, const double* __restrict__ q, const doubl
             double tau_prev = 0.0, dt_prev = 1.0;
             for (int jt = 0; jt < seg; ++jt) {
                 const int64_t t = t0 + jt;
-                __syncwarp();
-                if (t >= t1) continue;
-                // compiler barrier: the table is re-read from shared memory where it is used instead of
-                // being hoisted out of the loop into ~40 live registers
-                asm volatile("" ::: "memory");
-                const double tau = epoch_tau(ep, t, t0m, tEm);
-                const double ratio = epoch_ratio(ep, tau, tau_prev, dt_prev, st);
-                // zeta_cm = (tau + i u0) (cos a + i sin a), then shift to the primary frame
-                const double zx = __dadd_rn(__dadd_rn(__dmul_rn(tau, ms.ca), -ur1), -ms.shift);
-                const double zy = __dadd_rn(__dmul_rn(tau, ms.sa), ur0);
-                const cd zeta = mk(zx, zy);
+                const bool act = t < t1;
                 PointResult res;
                 res.flags = 0;
-                MLM_COUNT(positions);
-                advance_images(ms.T, zeta, sz, szp, szpp, MLM_MODELS_BLOCK, st, res.flags, ratio);
+                __syncwarp();                            // the lanes of a warp take every epoch together ...
+                if (act) {
+                    // compiler barrier: the table is re-read from shared memory where it is used instead of
+                    // being hoisted out of the loop into ~40 live registers
+                    asm volatile("" ::: "memory");
+                    const double tau = TIMES ? epoch_tau(ep, t, t0m, tEm) : __dadd_rn(ep.tau0, __dmul_rn((double)t, ep.dtau));
+                    const double ratio = TIMES ? epoch_ratio(ep, tau, tau_prev, dt_prev, st) : 1.0;
+                    // zeta_cm = (tau + i u0) (cos a + i sin a), then shift to the primary frame
+                    const double zx = __dadd_rn(__dadd_rn(__dmul_rn(tau, ms.ca), -ur1), -ms.shift);
+                    const double zy = __dadd_rn(__dmul_rn(tau, ms.sa), ur0);
+                    MLM_COUNT(positions);
+                    advance_images(ms.T, mk(zx, zy), sz, szp, szpp, MLM_MODELS_BLOCK, st, res.flags, ratio);
+                }
+                __syncwarp();                            // ... and meet again before the image sums
+                if (!act) continue;
                 sum_images<ORDER>(ms.T, ms.sf, sz, MLM_MODELS_BLOCK, st.nimg, res);
                 store_result(res, m * Tn + t, A0, A2, A4, nimg, flags);
             }
@@ -496,11 +505,11 @@ k_models(const double* __restrict__ s, const double* __restrict__ q, const doubl
 // w_t = 1/sigma_t^2; a fixed-order tree reduction over the P threads makes the result deterministic.  Output per
 // model (8 doubles):
 //   chi2 (minimised over Fs, Fb), Fs, Fb, sum w A, sum w A^2, sum w A f, #epochs with 5 images, #flagged epochs
-template <int ORDER>
-__global__ void __launch_bounds__(MLM_MODELS_BLOCK, 6)
+template <int ORDER, bool TIMES>
+__global__ void __launch_bounds__(MLM_MODELS_BLOCK, MLM_CHI2_MINBLOCKS)
 k_models_chi2(const double* __restrict__ s, const double* __restrict__ q, const double* __restrict__ rho,
               const double* __restrict__ Gamma, const double* __restrict__ u0, const double* __restrict__ alpha,
-              int64_t M, const Epochs ep, int64_t Tn, int seg, int P, const double* __restrict__ flux,
+              int64_t M, const __grid_constant__ Epochs ep, int64_t Tn, int seg, int P, const double* __restrict__ flux,
               const double* __restrict__ weight, double* __restrict__ stats) {
     __shared__ ModelSlot slots[MLM_MODELS_GMAX];
     __shared__ cd s_roots[3][5][MLM_MODELS_BLOCK];
@@ -523,7 +532,7 @@ k_models_chi2(const double* __restrict__ s, const double* __restrict__ q, const 
             const ModelSlot& ms = slots[have_model ? g : 0];
             const double u = have_model ? u0[m] : 0.0;
             const double ur1 = __dmul_rn(u, ms.sa), ur0 = __dmul_rn(u, ms.ca);
-            const double t0m = (have_model && ep.t0) ? ep.t0[m] : 0.0, tEm = (have_model && ep.tE) ? ep.tE[m] : 1.0;
+            const double t0m = (TIMES && have_model && ep.t0) ? ep.t0[m] : 0.0, tEm = (TIMES && have_model && ep.tE) ? ep.tE[m] : 1.0;
             for (int64_t sbase = 0; sbase < nseg; sbase += P) {      // block-uniform trip counts, see k_models
                 const int64_t sg = sbase + lane;
                 const int64_t t0 = sg * seg;
@@ -533,18 +542,21 @@ k_models_chi2(const double* __restrict__ s, const double* __restrict__ q, const 
                 double tau_prev = 0.0, dt_prev = 1.0;
                 for (int jt = 0; jt < seg; ++jt) {
                     const int64_t t = t0 + jt;
-                    __syncwarp();
-                    if (t >= t1) continue;
-                    asm volatile("" ::: "memory");
-                    const double tau = epoch_tau(ep, t, t0m, tEm);
-                    const double ratio = epoch_ratio(ep, tau, tau_prev, dt_prev, st);
-                    const double zx = __dadd_rn(__dadd_rn(__dmul_rn(tau, ms.ca), -ur1), -ms.shift);
-                    const double zy = __dadd_rn(__dmul_rn(tau, ms.sa), ur0);
-                    const cd zeta = mk(zx, zy);
+                    const bool act = t < t1;
                     PointResult res;
                     res.flags = 0;
-                    MLM_COUNT(positions);
-                    advance_images(ms.T, zeta, sz, szp, szpp, MLM_MODELS_BLOCK, st, res.flags, ratio);
+                    __syncwarp();
+                    if (act) {
+                        asm volatile("" ::: "memory");
+                        const double tau = TIMES ? epoch_tau(ep, t, t0m, tEm) : __dadd_rn(ep.tau0, __dmul_rn((double)t, ep.dtau));
+                        const double ratio = TIMES ? epoch_ratio(ep, tau, tau_prev, dt_prev, st) : 1.0;
+                        const double zx = __dadd_rn(__dadd_rn(__dmul_rn(tau, ms.ca), -ur1), -ms.shift);
+                        const double zy = __dadd_rn(__dmul_rn(tau, ms.sa), ur0);
+                        MLM_COUNT(positions);
+                        advance_images(ms.T, mk(zx, zy), sz, szp, szpp, MLM_MODELS_BLOCK, st, res.flags, ratio);
+                    }
+                    __syncwarp();
+                    if (!act) continue;
                     sum_images<ORDER>(ms.T, ms.sf, sz, MLM_MODELS_BLOCK, st.nimg, res);
                     const double A = (ORDER >= 4) ? res.A4 : res.A2;
                     const double w = __ldg(weight + t), f = __ldg(flux + t);
@@ -1236,9 +1248,9 @@ static int launch_models(mlm_context* ctx, const char* who, const double* s, con
     dim3 grid((unsigned)bx, (unsigned)(nmb < 65535 ? nmb : 65535));
     cudaStream_t st = pick(ctx, stream);
     if (order == 4)
-        k_models<4><<<grid, MLM_MODELS_BLOCK, 0, st>>>(s, q, rho, Gamma, u0, alpha, M, ep, Tn, seg, P, A0, A2, A4, nimg, flags);
+        (ep.times ? k_models<4, true> : k_models<4, false>)<<<grid, MLM_MODELS_BLOCK, 0, st>>>(s, q, rho, Gamma, u0, alpha, M, ep, Tn, seg, P, A0, A2, A4, nimg, flags);
     else
-        k_models<2><<<grid, MLM_MODELS_BLOCK, 0, st>>>(s, q, rho, Gamma, u0, alpha, M, ep, Tn, seg, P, A0, A2, A4, nimg, flags);
+        (ep.times ? k_models<2, true> : k_models<2, false>)<<<grid, MLM_MODELS_BLOCK, 0, st>>>(s, q, rho, Gamma, u0, alpha, M, ep, Tn, seg, P, A0, A2, A4, nimg, flags);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -1262,14 +1274,31 @@ int mlm_models_times(mlm_context* ctx, const double* s, const double* q, const d
                          A4, nimg, flags, stream);
 }
 
-// Epochs per warm-start segment for a grid of M models x Tn epochs: long segments (few cold solves: one per
-// segment, ~2.5 tracked epochs each) as long as the grid still fills the GPU about twice (sm_count x 6 blocks x 64
-// threads resident), between 4 and 128 epochs.
+// Epochs per warm-start segment for a grid of M models x Tn epochs.  A segment is a serial chain (one thread, ~7 us per
+// epoch) and a block of 64 threads is the unit of scheduling, so a launch needs MANY more blocks than fit on the GPU at
+// once or its tail dominates.  Measured on the C5 grid (2e7 positions; rounds = blocks / resident blocks): 128-epoch
+// segments (2.1 rounds) 4.0 ms, 64 (4.2) 3.03 ms, 32 (8.4) 2.98 ms, 16 (17; eight times the cold solves of 128)
+// 2.89 ms -- and 24 or 48 epochs, which leave a light curve with a number of segments just above a power of two
+// (84, 42: the threads of a model are a power of two), 3.40 and 4.21 ms.  Rule: ~8 segments per resident thread
+// (sm_count x MLM_MODELS_MINBLOCKS blocks x 64 threads) -- but not below 16 epochs (a cold solve costs ~3 tracked
+// epochs) while 16-epoch segments still give two rounds -- snapped to Tn / 2^k, between 4 and 128 epochs.
 static int auto_segment(int sm_count, int64_t M, int64_t Tn) {
-    const int64_t resident = (int64_t)sm_count * 6 * MLM_MODELS_BLOCK;
-    int64_t seg = (M * Tn + 2 * resident - 1) / (2 * resident);
-    if (seg > Tn) seg = Tn;
-    return (int)(seg < 4 ? 4 : (seg > 128 ? 128 : seg));
+    const int64_t resident = (int64_t)sm_count * MLM_MODELS_MINBLOCKS * MLM_MODELS_BLOCK;
+    double target = (double)(M * Tn) / (8.0 * (double)resident);
+    const double two_rounds = (double)(M * Tn) / (2.0 * (double)resident);
+    if (target < 16.0) target = fmax(target, fmin(16.0, two_rounds));
+    target = target < 4.0 ? 4.0 : (target > 128.0 ? 128.0 : target);
+    int64_t best = 0;
+    double best_err = 1e300;
+    for (int k = 0; k < 40 && ((int64_t)1 << k) <= Tn; ++k) {
+        const int64_t n = (int64_t)1 << k, sk = (Tn + n - 1) / n;      // 2^k segments of sk epochs
+        if (sk > 128) continue;
+        if (sk < 4) break;
+        const double err = fabs(log((double)sk / target));
+        if (err < best_err) { best_err = err; best = sk; }
+    }
+    if (best == 0) best = (int64_t)target < Tn ? (int64_t)target : Tn;   // Tn < 4 (or no admissible power of two)
+    return (int)(best < 1 ? 1 : best);
 }
 
 static int models_segment(mlm_context* ctx, int seg, int64_t M, int64_t Tn) {
@@ -1306,9 +1335,9 @@ static int launch_models_chi2(mlm_context* ctx, const char* who, const double* s
     const unsigned blocks = (unsigned)(nmb < 1048576 ? nmb : 1048576);
     cudaStream_t st = pick(ctx, stream);
     if (order == 4)
-        k_models_chi2<4><<<blocks, MLM_MODELS_BLOCK, 0, st>>>(s, q, rho, Gamma, u0, alpha, M, ep, Tn, seg, P, flux, weight, stats);
+        (ep.times ? k_models_chi2<4, true> : k_models_chi2<4, false>)<<<blocks, MLM_MODELS_BLOCK, 0, st>>>(s, q, rho, Gamma, u0, alpha, M, ep, Tn, seg, P, flux, weight, stats);
     else
-        k_models_chi2<2><<<blocks, MLM_MODELS_BLOCK, 0, st>>>(s, q, rho, Gamma, u0, alpha, M, ep, Tn, seg, P, flux, weight, stats);
+        (ep.times ? k_models_chi2<2, true> : k_models_chi2<2, false>)<<<blocks, MLM_MODELS_BLOCK, 0, st>>>(s, q, rho, Gamma, u0, alpha, M, ep, Tn, seg, P, flux, weight, stats);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;

@@ -11,7 +11,8 @@
    nimg - ((flags >> 6) & 3) == the reference's count (the kernel kept an image that the plain 1e-6 test of
    multipoles.py:183 rejects on its own roots), or lie in rule 3's mask (the REFERENCE's root residual is within a
    decade of its threshold: np.roots' unpolished root fails the test that the kernel's polished root passes);
-   the number of disputes is capped (default 1 % of the sample).
+   the number of disputes OUTSIDE rule 3's mask is capped (default 1 % of the sample); those inside it are positions
+   the rules exclude (the reference's own answer is unreliable there) and are only reported and adjudicated.
 """
 from __future__ import annotations
 
@@ -39,7 +40,8 @@ def compare(got_n, got_A, ref_n, ref_A, mask=None, truth_fn=None, max_adjudicate
 
     got_A/ref_A: (n,3) arrays.  truth_fn(i) -> (n_truth, A0, A2, A4) for rule 4 (optional).
     got_flags: the kernel's flag bytes (rule 5; None skips the accounting of count disputes).
-    max_adjudicate: cap on the number of disputes (default max_dispute_frac of the sample, at least 8).
+    max_adjudicate: how many disputes are adjudicated at most (default max_dispute_frac of the sample, at least 8; in
+    strict mode more disputes than that fail); max_dispute_frac: cap on the disputes outside the mask.
     """
     got_n = np.asarray(got_n).astype(np.int64).ravel()
     ref_n = np.asarray(ref_n).astype(np.int64).ravel()
@@ -88,7 +90,10 @@ def compare(got_n, got_A, ref_n, ref_A, mask=None, truth_fn=None, max_adjudicate
         require(unmasked_disputes == 0, "unmasked_disputes_without_adjudicator",
                 f"{unmasked_disputes} unmasked parity disputes, no adjudicator: {report}")
         return report
-    require(len(disputed) <= max_adjudicate, "too_many_disputes", f"too many disputes to adjudicate ({len(disputed)}): {report}")
+    cap = max(8, int(np.ceil(max_dispute_frac * n)))
+    require(unmasked_disputes <= cap, "too_many_disputes", f"{unmasked_disputes} disputes outside the mask (cap {cap}): {report}")
+    if strict:
+        require(len(disputed) <= max_adjudicate, "too_many_to_adjudicate", f"too many disputes to adjudicate ({len(disputed)}): {report}")
     if len(disputed) > max_adjudicate:
         disputed = np.sort(np.random.default_rng(1).choice(disputed, max_adjudicate, replace=False))
         report["adjudicated_subset_of"] = int(np.sum(bad_n | bad_v))

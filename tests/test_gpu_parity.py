@@ -363,7 +363,7 @@ def test_models_chi2_fused_fit(mb):
     assert np.allclose(r2["SA"], (w[None, :] * lc["A2"]).sum(axis=1), rtol=1e-10)
     # long segments: 700 epochs in segments of 100 -> 8 threads per model, 8 models share a block of 64 threads
     # (what a 1e4-model grid gets); same light curves to rounding, same statistics from them
-    assert mb._capi.context().auto_segment(10000, 2000) == 128 and mb._capi.context().auto_segment(1, 1000000) <= 16
+    assert mb._capi.context().auto_segment(10000, 2000) == 32 and mb._capi.context().auto_segment(1, 1000000) <= 16
     for seg in (100, 350, 700):
         lcs = mb.magnification_models(s, q, rho, G, u0, al, tau0, dtau, T, segment=seg)
         assert np.array_equal(lcs["nimg"], lc["nimg"]), seg

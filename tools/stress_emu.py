@@ -9,7 +9,7 @@ import check_emu as ce
 libs = ctypes.CDLL(_ROOT + '/tests/host_emu/libmlm_emu_stats.so')
 def run(name,s,q,rho,G,zeta):
     ce.lib = libs
-    st=np.zeros(2,np.int64); libs.emu_stats(st.ctypes.data_as(ctypes.POINTER(ctypes.c_long)),1)
+    st=np.zeros(4,np.int64); libs.emu_stats(st.ctypes.data_as(ctypes.POINTER(ctypes.c_long)),1)
     t=time.time(); ni,A0,A2,A4,fl=ce.emu_points(s,q,rho,G,zeta); te=time.time()-t
     libs.emu_stats(st.ctypes.data_as(ctypes.POINTER(ctypes.c_long)),1)
     nb,B0,B2,B4,z,keep,minJ,res=o.batch_a4(s,q,rho,G,zeta,return_extra=True)
