@@ -959,6 +959,115 @@ MLM_HD void sum_images(const LensTable& T, const SourceFactors sf, const cd* sz,
     out.A0 = A0; out.A2 = A2; out.A4 = A4; out.nimg = (unsigned)nimg; out.flags = flags;
 }
 
+// ---------------------------------------------------------------------------------------
+// Cold start WITHOUT the root finder (k_points_direct: lists of unrelated positions).
+//
+// A binary lens always has (at least) three images, and they sit where three single-lens problems put them: next to
+// either lens the minor image of that lens alone (the other lens acting as a constant deflection), and outside the
+// major image of the total mass at the centre of mass.  Newton on the LENS EQUATION from these three guesses
+// (~3 evaluations of 55 FP64 instructions each) gives three images at rounding level -- if it converges on three
+// DISTINCT points they are solutions of the lens equation, hence roots of the quintic, whatever the guesses were --
+// and the other two roots of the quintic follow from Vieta (a quadratic), polished on the quintic.  The five roots
+// then take the usual classification (classify_roots).  ~1 000 FP64 instructions instead of ~3 400 for Laguerre +
+// deflation + polish.  Where the guesses fail (inside and next to resonant caustics the three-point picture is wrong;
+// the source on a lens; degenerate polynomial) the function answers false and the caller solves the position with
+// the root finder: the result never depends on a guess having been good.
+//
+// `extra`: number of the three images whose own POLYNOMIAL root would fail the plain |residual| < 1e-6 test of
+// multipoles.py:183 (the count MLM_FLAG_EXTRA reports): an image next to a lens (|W2| > 1e3) is moved by one Newton
+// step on the quintic -- onto the root as the rounding noise of the polynomial defines it, which is what a root
+// finder returns -- and tested there (MLM_FLAG_AMBIG likewise).  The flags are then those of the root-finder path
+// in distribution, not position by position: they report rounding noise.
+// ---------------------------------------------------------------------------------------
+MLM_HD cd point_lens_image(cd u, double m, double sign) {        // u (1 + sign sqrt(1 + 4 m / |u|^2)) / 2
+    const double n = norm2(u);
+    const double t = 1.0 + 4.0 * m * rcp(n);
+    const double f = 0.5 * (1.0 + sign * (t * rsqrt_(t)));
+    return scale(f, u);
+}
+
+MLM_HD bool guess_solve(const LensTable& T, cd zeta, cd* sz, int stride, int& extra, unsigned& flags) {
+    extra = 0;
+    cd c[6];
+    lens_polynomial(T, zeta, c);
+    if (c[5].x == 0.0 && c[5].y == 0.0) return false;
+    const double m1 = T.alpha[1], m2 = T.beta[1], is = rcp(T.s);
+    cd sum = mk(0.0, 0.0);
+    double mag = 1.0;
+    bool ok = true;
+#pragma unroll 1
+    for (int k = 0; k < 3; ++k) {
+        cd zk;
+        if (k == 0) zk = point_lens_image(mk(zeta.x + m2 * is, zeta.y), m1, -1.0);
+        else if (k == 1) zk = mk(-T.s, 0.0) + point_lens_image(mk(zeta.x - m1 * is + T.s, zeta.y), m2, -1.0);
+        else zk = mk(-T.s * m2, 0.0) + point_lens_image(mk(zeta.x + T.s * m2, zeta.y), 1.0, 1.0);
+        bool conv = false;
+        double lim = 1e300;
+#pragma unroll 1
+        for (int it = 0; it < 10; ++it) {
+            double dz2, z2, zs2;
+            const cd zn = lens_newton(T, zeta, zk, dz2, z2, zs2);
+            MLM_COUNT(lens_evals);
+            if (!(dz2 < lim)) break;
+            zk = zn;
+            if (dz2 <= 1e-14 * z2 && (dz2 <= 1e-14 * zs2 || dz2 <= 3.2e-30 * z2)) { conv = true; break; }
+            lim = 0.25 * dz2;                            // every step at most half the one before
+        }
+        ok = ok && conv;
+        sz[k * stride] = zk;
+        sum = sum + zk;
+        mag += norm2(zk);
+    }
+    if (!ok) return false;
+    const cd z0 = sz[0], z1 = sz[stride], z2 = sz[2 * stride];
+    const double tol = 1e-12 * mag;
+    if (!(norm2(z0 - z1) > tol && norm2(z0 - z2) > tol && norm2(z1 - z2) > tol)) return false;
+    // the other two roots: r4 + r5 = S, r4 r5 = P
+    const cd ic5 = crcp(c[5]);
+    const cd S = -(cfma(c[4], ic5, sum));
+    const cd P = -(cmul(cmul(c[0], ic5), crcp(cmul(cmul(z0, z1), z2))));
+    cd sq = csqrt_(rfma(-4.0, P, csq(S)));
+    if (re_mulc(S, sq) < 0.0) sq = -sq;
+    cd r4 = scale(0.5, S + sq);
+    cd r5 = cmul(P, crcp(r4));
+    if (!(quintic_newton(c, T.s, r4) && quintic_newton(c, T.s, r5))) return false;
+    // five distinct roots?  (Vieta on the polished pair)
+    const cd v = cfma(c[4], ic5, sum + r4 + r5);
+    if (!(norm2(v) <= 1e-16 * (mag + norm2(r4) + norm2(r5)))) return false;
+    sz[3 * stride] = r4;
+    sz[4 * stride] = r5;
+    // images next to a lens: would their polynomial root pass the plain test?
+#pragma unroll 1
+    for (int k = 0; k < 3; ++k) {
+        const cd zk = sz[k * stride];
+        const double d2 = fmin(norm2(zk), norm2(mk(zk.x + T.s, zk.y)));
+        if (d2 < 1e-3) {                                 // |W2| = m / d^2 > 1e3 m
+            double dz2;
+            const cd zq = newton_step(c, zk, dz2);
+            const double f2 = lens_residual2(T, zeta, zq);
+            if (f2 > 1e-14 && f2 < 1e-10) flags |= MLM_FLAG_AMBIG;      // like classify_roots on a polynomial root
+            if (!(f2 < 1e-12)) ++extra;
+        }
+    }
+    return true;
+}
+
+// whole path for one source position from the three-image guesses; false: not solved this way (nothing valid in out)
+template <int ORDER>
+MLM_HD bool point_magnification_direct(const LensTable& T, const SourceFactors sf, cd zeta, cd* sz, int stride,
+                                       PointResult& out) {
+    int extra_g = 0, extra_c = 0;
+    out.flags = 0;
+    if (!guess_solve(T, zeta, sz, stride, extra_g, out.flags)) return false;
+    MLM_COUNT(classify_calls);
+    const int nimg = classify_roots(T, zeta, sz, stride, out.flags, extra_c);
+    if (nimg < 3) return false;                          // cannot happen with three converged images; be safe
+    const int extra = extra_g + extra_c;
+    if (extra) out.flags |= MLM_FLAG_EXTRA | ((unsigned)(extra < 3 ? extra : 3) << MLM_FLAG_EXTRA_SHIFT);
+    sum_images<ORDER>(T, sf, sz, stride, nimg, out);
+    return true;
+}
+
 // whole path for one source position (cold start)
 template <int ORDER>
 MLM_HD PointResult point_magnification(const LensTable& T, const SourceFactors sf, cd zeta) {

@@ -235,6 +235,68 @@ __global__ void __launch_bounds__(256) k_curve_keys(const double2* __restrict__ 
     idx[i] = (uint32_t)i;
 }
 
+// K1e: list of UNRELATED positions (mlm_points_unordered), one position per thread, nothing carried between entries --
+// the result of an entry does not depend on the rest of the list.  First pass (k_points_direct): the three images that
+// every binary-lens configuration has, by Newton on the lens equation from single-lens guesses, the other two roots of
+// the quintic by Vieta (point_magnification_direct, ~1 500 FP64 instructions with the sums).  Entries that this does
+// not solve (inside and next to resonant caustics, ~1 % of a planetary light curve, half of a map window centred on a
+// resonant caustic) are appended to a work list -- one atomicAdd per warp -- instead of being solved on the spot with
+// 31 lanes waiting, and the second pass (k_points_list) runs the root finder (Laguerre + deflation + polish,
+// ~4 600 warp-level instructions per entry) on the COMPACTED list with full warps.
+template <int ORDER>
+__global__ void __launch_bounds__(MLM_BLOCK, 4)
+k_points_direct(const __grid_constant__ LensTable T, const SourceFactors sf, const double2* __restrict__ zeta, int64_t n,
+                uint32_t* __restrict__ worklist, unsigned* __restrict__ counter, double* __restrict__ A0,
+                double* __restrict__ A2, double* __restrict__ A4, uint8_t* __restrict__ nimg, uint8_t* __restrict__ flags) {
+    __shared__ cd s_roots[5][MLM_BLOCK];
+    cd* const sz = &s_roots[0][threadIdx.x];
+    const int64_t i = (int64_t)blockIdx.x * MLM_BLOCK + threadIdx.x;
+    const bool act = i < n;
+    bool solved = true;
+    PointResult r;
+    r.flags = 0;
+    if (act) {
+        const double2 zz = __ldg(zeta + i);
+        MLM_COUNT(positions);
+        solved = point_magnification_direct<ORDER>(T, sf, mk(zz.x, zz.y), sz, MLM_BLOCK, r);
+        if (solved) store_result(r, i, A0, A2, A4, nimg, flags);
+    }
+    __syncwarp();
+    const unsigned fail = __ballot_sync(0xffffffffu, !solved);
+    if (fail) {
+        const int lane = threadIdx.x & 31;
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(counter, (unsigned)__popc(fail));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (!solved) worklist[base + __popc(fail & ((1u << lane) - 1u))] = (uint32_t)i;
+    }
+}
+
+template <int ORDER>
+__global__ void __launch_bounds__(MLM_BLOCK, 4)
+k_points_list(const __grid_constant__ LensTable T, const SourceFactors sf, const double2* __restrict__ zeta,
+              const uint32_t* __restrict__ worklist, const unsigned* __restrict__ counter, double* __restrict__ A0,
+              double* __restrict__ A2, double* __restrict__ A4, uint8_t* __restrict__ nimg, uint8_t* __restrict__ flags) {
+    __shared__ cd s_roots[5][MLM_BLOCK];
+    cd* const sz = &s_roots[0][threadIdx.x];
+    const unsigned cnt = __ldg(counter);
+    for (unsigned j0 = blockIdx.x * MLM_BLOCK; j0 < cnt; j0 += gridDim.x * MLM_BLOCK) {
+        const unsigned j = j0 + threadIdx.x;
+        __syncwarp();
+        if (j >= cnt) continue;
+        const int64_t i = (int64_t)__ldg(worklist + j);
+        const double2 zz = __ldg(zeta + i);
+        PointResult r;
+        r.flags = 0;
+        TrackState st;
+        st.hist = 0; st.nimg = 0; st.extra = 0;
+        MLM_COUNT(positions);
+        advance_images(T, mk(zz.x, zz.y), sz, sz, nullptr, MLM_BLOCK, st, r.flags);
+        sum_images<ORDER>(T, sf, sz, MLM_BLOCK, st.nimg, r);
+        store_result(r, i, A0, A2, A4, nimg, flags);
+    }
+}
+
 // K1b: magnification map, zeta generated in-kernel (no input traffic).
 // blockIdx.x tiles the columns; blockIdx.y strides over STRIPS of `strip` consecutive rows
 // (aligned to absolute row numbers, so any row-sharding on multiples of `strip` reproduces the
@@ -763,6 +825,7 @@ struct mlm_context {
     // caller's stream and touch no context state.
     std::recursive_mutex mu;
     int anchor_segment = 16;                           // columns per thread of k_anchor (MLM_MAP_ANCHOR; 0: no anchors, cold strip starts)
+    int unordered_sorted = 0;                          // MLM_UNORDERED=sorted: mlm_points_unordered visits the list along a Hilbert curve (tracking) instead of solving every entry on its own
     int u8rows_env = -1;                               // MLM_MAP_U8ROWS = 0/1 forces the row-wise one-byte stores off/on (experiments)
     int points_segment = 0;                            // consecutive list entries per thread of k_points (0: from n; MLM_POINTS_SEGMENT)
     int models_segment = 0;                            // epochs per warm-start segment of k_models (0: from T; MLM_SEGMENT)
@@ -861,6 +924,7 @@ int mlm_create(int device, mlm_context** out) {
         if (v >= 1 && v <= 4096) ctx->map_strip_env = v;
     }
     if (const char* e6 = getenv("MLM_MAP_U8ROWS")) ctx->u8rows_env = atoi(e6) ? 1 : 0;
+    if (const char* e7 = getenv("MLM_UNORDERED")) ctx->unordered_sorted = (strcmp(e7, "sorted") == 0);
     if (const char* e5 = getenv("MLM_MAP_ANCHOR")) {
         const int v = atoi(e5);
         if (v >= 0 && v <= 4096) ctx->anchor_segment = v;
@@ -1069,6 +1133,33 @@ int mlm_points_unordered(mlm_context* ctx, double s, double q, double rho, doubl
     if (n < 4096) return mlm_points(ctx, s, q, rho, Gamma, zeta, n, order, A0, A2, A4, nimg, flags, stream);
     DeviceGuard g(ctx->device);
     cudaStream_t st = pick(ctx, stream);
+    if (!ctx->unordered_sorted) {
+        // every entry on its own: three-image guesses, then the root finder on the compacted rest
+        LensTable T;
+        make_table(s, q, &T);
+        const SourceFactors sf = source_factors(rho, Gamma);
+        char* ws = nullptr;
+        CK(cudaMallocAsync((void**)&ws, 256 + (size_t)n * sizeof(uint32_t), st));
+        unsigned* counter = (unsigned*)ws;
+        uint32_t* worklist = (uint32_t*)(ws + 256);
+        cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned), st);
+        if (e == cudaSuccess) {
+            const unsigned blocks = (unsigned)((n + MLM_BLOCK - 1) / MLM_BLOCK);
+            const unsigned blocks2 = blocks < (unsigned)ctx->sm_count * 8u ? blocks : (unsigned)ctx->sm_count * 8u;
+            if (order == 4) {
+                k_points_direct<4><<<blocks, MLM_BLOCK, 0, st>>>(T, sf, (const double2*)zeta, n, worklist, counter, A0, A2, A4, nimg, flags);
+                k_points_list<4><<<blocks2, MLM_BLOCK, 0, st>>>(T, sf, (const double2*)zeta, worklist, counter, A0, A2, A4, nimg, flags);
+            } else {
+                k_points_direct<2><<<blocks, MLM_BLOCK, 0, st>>>(T, sf, (const double2*)zeta, n, worklist, counter, A0, A2, A4, nimg, flags);
+                k_points_list<2><<<blocks2, MLM_BLOCK, 0, st>>>(T, sf, (const double2*)zeta, worklist, counter, A0, A2, A4, nimg, flags);
+            }
+            ctx->launches += 2;
+            e = cudaGetLastError();
+        }
+        cudaFreeAsync(ws, st);
+        if (e != cudaSuccess) return fail(ctx, (int)e, "mlm_points_unordered");
+        return 0;
+    }
     // stream-ordered scratch: bbox | keys in/out | indices in/out | CUB temporary storage
     size_t cub_bytes = 0;
     CK(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,

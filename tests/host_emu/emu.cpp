@@ -36,6 +36,25 @@ void emu_points(double s, double q, double rho, double Gamma, const double* zeta
     }
 }
 
+// the same through the three-image guesses (k_points_direct), falling back to the root finder like the kernels do;
+// used[i] = 1 where the guesses solved the position
+void emu_points_direct(double s, double q, double rho, double Gamma, const double* zeta, long n, int order,
+                       double* A0, double* A2, double* A4, unsigned char* nimg, unsigned char* flags, unsigned char* used) {
+    LensTable T;
+    make_table(s, q, &T);
+    SourceFactors sf = source_factors(rho, Gamma);
+    for (long i = 0; i < n; ++i) {
+        cd z = mk(zeta[2 * i], zeta[2 * i + 1]);
+        cd store[5];
+        PointResult r;
+        bool ok = (order >= 4) ? point_magnification_direct<4>(T, sf, z, store, 1, r) : point_magnification_direct<2>(T, sf, z, store, 1, r);
+        used[i] = ok ? 1 : 0;
+        if (!ok) r = (order >= 4) ? point_magnification<4>(T, sf, z) : point_magnification<2>(T, sf, z);
+        A0[i] = r.A0; A2[i] = r.A2; A4[i] = r.A4;
+        nimg[i] = (unsigned char)r.nimg; flags[i] = (unsigned char)r.flags;
+    }
+}
+
 void emu_roots(double s, double q, const double* zeta, long n, double* roots, unsigned char* flags) {
     LensTable T;
     make_table(s, q, &T);

@@ -142,6 +142,19 @@ def emu(built):
             return ni, np.stack(A, 1), fl
 
         @staticmethod
+        def points_direct(s, q, rho, G, zeta, order=4):
+            """control flow of mlm_points_unordered: three-image guesses, root finder where they fail"""
+            zeta = np.ascontiguousarray(zeta, dtype=np.complex128)
+            n = zeta.size
+            A = [np.zeros(n) for _ in range(3)]
+            ni, fl, used = np.zeros(n, np.uint8), np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+            lib.emu_points_direct(ctypes.c_double(s), ctypes.c_double(q), ctypes.c_double(rho), ctypes.c_double(G),
+                                  zeta.view(np.float64).ctypes.data_as(dp), ctypes.c_long(n), ctypes.c_int(order),
+                                  *[a.ctypes.data_as(dp) for a in A], ni.ctypes.data_as(up), fl.ctypes.data_as(up),
+                                  used.ctypes.data_as(up))
+            return ni, np.stack(A, 1), fl, used
+
+        @staticmethod
         def roots(s, q, zeta):
             zeta = np.ascontiguousarray(zeta, dtype=np.complex128)
             r = np.zeros((zeta.size, 5), np.complex128)
@@ -188,6 +201,47 @@ def test_logic_wirtinger_and_literal_recursions_agree_with_oracle(emu):
         got = emu.image_terms(W, literal)
         cond = 1 + np.abs(mu0)                  # near-critical images amplify rounding
         assert np.all(np.abs(got / ref - 1) < 1e-11 * cond[:, None] ** 2), literal
+
+
+def test_logic_direct_cold_start_equals_root_finder(emu, golden_points):
+    """mlm_points_unordered's first pass (three images by Newton on the lens equation from single-lens guesses, the
+    other two roots by Vieta) against the root-finder path: same image counts everywhere -- golden points, random
+    positions over q = 1e-7..1 and s = 0.3..3, the lens axis, a distant source, a source on top of a lens -- values to
+    1e-9 where unflagged; the guesses solve most of a planetary configuration and fall back inside resonant caustics."""
+    g = golden_points
+    keys = {}
+    for i, p in enumerate(map(tuple, g["params"])):
+        keys.setdefault(p, []).append(i)
+    solved = {}
+    for p, idx in keys.items():
+        idx = np.array(idx)
+        n0, A0, f0 = emu.points(*p, g["zeta"][idx])
+        n1, A1, f1, used = emu.points_direct(*p, g["zeta"][idx])
+        assert np.array_equal(n0, n1), p
+        ok = (f0 == 0) & (f1 == 0)
+        if ok.any():
+            assert np.nanmax(np.abs(A1[ok] / A0[ok] - 1)) < 1e-9, p
+        for t in np.unique(g["tags"][idx]):
+            solved.setdefault(str(t), []).append(used[g["tags"][idx] == t])
+    frac = {t: float(np.concatenate(v).mean()) for t, v in solved.items()}
+    assert frac["C2"] > 0.9 and frac["C5"] > 0.8, frac
+    rng = np.random.default_rng(17)
+    cases = []
+    for _ in range(10):
+        s, q = float(np.exp(rng.uniform(np.log(0.3), np.log(3)))), float(np.exp(rng.uniform(np.log(1e-7), 0)))
+        cases.append((s, q, rng.uniform(-2, 2, 3000) + 1j * rng.uniform(-2, 2, 3000)))
+    s, q = 1.2, 1e-5
+    cases += [(s, q, rng.uniform(-3, 3, 2000) + 0j), (s, q, 1e3 * (rng.uniform(-1, 1, 2000) + 1j * rng.uniform(-1, 1, 2000))),
+              (s, q, -s + 1e-3 * (rng.uniform(-1, 1, 2000) + 1j * rng.uniform(-1, 1, 2000))),
+              (1.0, 0.5, np.array([0.0, -1.0, 1e-300, -1.0 + 1e-12j, complex(np.nan, 0.0), 1e6, -300j]))]
+    for s, q, z in cases:
+        n0, A0, f0 = emu.points(s, q, 1e-3, 0.5, z)
+        n1, A1, f1, used = emu.points_direct(s, q, 1e-3, 0.5, z)
+        assert np.array_equal(n0, n1), (s, q)
+        ok = (f0 == 0) & (f1 == 0) & np.isfinite(A0[:, 2])
+        if ok.any():
+            assert np.max(np.abs(A1[ok] / A0[ok] - 1)) < 1e-9, (s, q)
+        assert not ((f1 & 1) & ~(f0 & 1)).any()              # no iteration cap hit where the root finder hits none
 
 
 def test_logic_golden_points_parity(emu, golden_points):
