@@ -885,8 +885,13 @@ def other_configs(mb, dev, rank, world, barrier, reps=3):
     timed(lambda: points_device(c["s"], c["q"], c["rho"], c["Gamma"], zeta, T2, *b, stream=st), T2,
           "C2_lightcurve_1e6_points", {"kernel": "k_points<4> (ordered list: tracked along consecutive entries)"})
     zsh = torch.from_numpy(zh[np.random.default_rng(1).permutation(T2)]).to(dev)
+    timed(lambda: points_device(c["s"], c["q"], c["rho"], c["Gamma"], zsh, T2, *b, stream=st, unordered=True), T2,
+          "C2_lightcurve_1e6_points_shuffled",
+          {"kernel": "k_points_direct<4> + k_points_list<4> (mlm_points_unordered: every entry solved on its own from "
+                     "three single-lens image guesses, root finder on the compacted rest)"})
     timed(lambda: points_device(c["s"], c["q"], c["rho"], c["Gamma"], zsh, T2, *b, stream=st), T2,
-          "C2_lightcurve_1e6_points_shuffled", {"kernel": "k_points<4> (unordered list: one cold solve per entry)"})
+          "C2_lightcurve_1e6_points_shuffled_tracking_kernel",
+          {"kernel": "k_points<4> on the same shuffled list (every entry a cold solve with the root finder, divergent lanes)"})
     # C5 through the host API with the fit fused (8 doubles per model leave the GPU)
     sv, qv, rv, gv, uv, av = par
     sig = np.full(T, 0.01)

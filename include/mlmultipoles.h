@@ -115,11 +115,14 @@ int mlm_auto_strip(mlm_context* ctx, int64_t nx, int64_t nrows);
 int mlm_points(mlm_context* ctx, double s, double q, double rho, double Gamma,
                const double* zeta, int64_t n, int order,
                double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags, void* stream);
-/* The same for a list WITHOUT spatial order (random positions, a shuffled catalogue): the entries are visited along
- * a space-filling curve (Hilbert-curve keys on a 65536^2 grid over their bounding box, radix-sorted on the device), so that
- * consecutive visits are neighbours in the source plane and the images can be carried from one to the next instead of
- * a cold solve per entry; results land at the entries' own indices.  n < 2^32.  Worth it when fewer than about half of
- * the consecutive entries are within 0.02 Einstein radii of each other (mlm_points_host checks a sample and picks). */
+/* The same for a list WITHOUT spatial order (random positions, a shuffled catalogue): every entry is solved on its
+ * own, nothing is carried between entries, so the result of an entry does not depend on the rest of the list.  First
+ * pass: the three images every binary-lens configuration has, by Newton on the lens equation from single-lens guesses,
+ * the other two roots of the quintic by Vieta; entries that this does not solve (inside and next to resonant caustics)
+ * are compacted into a work list and solved by the root finder (Laguerre + deflation + polish) in a second launch.
+ * Image counts equal mlm_points' cold solve, values to rounding; MLM_FLAG_EXTRA / MLM_FLAG_AMBIG report polynomial
+ * rounding noise and agree with the root-finder path in distribution, not position by position.  n < 2^32.
+ * mlm_points_host checks a sample of the list for coherence and picks between the two. */
 int mlm_points_unordered(mlm_context* ctx, double s, double q, double rho, double Gamma,
                          const double* zeta, int64_t n, int order,
                          double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags, void* stream);

@@ -218,8 +218,8 @@ def _p(x):
 
 def points_device(s, q, rho, Gamma, zeta, n, A0, A2, A4, nimg=None, flags=None, order=4, stream=None, device=None,
                   unordered=False):
-    """unordered=True: the list has no spatial order -- visit it along a space-filling curve (mlm_points_unordered:
-    device radix sort of Hilbert-curve keys) so that the images can be carried between neighbours."""
+    """unordered=True: the list has no spatial order -- every entry is solved on its own (mlm_points_unordered: three
+    single-lens image guesses + Newton on the lens equation, the root finder on the compacted rest)."""
     ctx = _capi.context(device)
     fn, name = (ctx.lib.mlm_points_unordered, "mlm_points_unordered") if unordered else (ctx.lib.mlm_points, "mlm_points")
     ctx.check(fn(ctx.handle, s, q, rho, Gamma, _p(zeta), n, order, _p(A0), _p(A2), _p(A4), _p(nimg), _p(flags), _p(stream)),

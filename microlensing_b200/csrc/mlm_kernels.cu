@@ -10,7 +10,6 @@
 //
 // Reference interfaces replaced: see include/mlmultipoles.h.
 #include <cuda_runtime.h>
-#include <cub/device/device_radix_sort.cuh>
 
 #include <atomic>
 #include <cmath>
@@ -77,18 +76,14 @@ __device__ __forceinline__ void store_result(const PointResult& r, int64_t i, do
 // entries that are far from their predecessor (> 0.02 Einstein radii), or whose tracking is
 // rejected, are solved cold, so an unordered list costs one cold solve per entry.  seg is a function of n
 // only; the 16-byte loads of a warp are seg entries apart (sector-granular, the path is compute-bound).
-// `perm` (optional): the list is visited in the order perm[0], perm[1], ... (mlm_points_unordered: the entries sorted
-// along a space-filling curve, so that consecutive visits are neighbours in the source plane); loads and stores go
-// to the entries' own places.
-// perm_close / perm_need (with perm): the sorted order is used only if at least perm_need of the SAMPLED consecutive
-// pairs of it are neighbours (k_perm_check) -- a list too sparse for that is visited in its own order, cold.
+// (Lists WITHOUT order go through k_points_direct / k_points_list below.  Visiting them along a Hilbert curve through the
+// source plane -- radix sort of curve keys, then this kernel along the sorted order -- was built and measured: slower
+// than a cold solve per entry on every list tried except a shuffled light curve, and 2.3-4x slower than the direct path.)
 template <int ORDER>
 __global__ void __launch_bounds__(MLM_BLOCK, 4)
 k_points(const __grid_constant__ LensTable T, const SourceFactors sf, const double2* __restrict__ zeta, int64_t n,
-         int seg, const uint32_t* __restrict__ perm, const unsigned* __restrict__ perm_close, unsigned perm_need,
-         double* __restrict__ A0, double* __restrict__ A2,
+         int seg, double* __restrict__ A0, double* __restrict__ A2,
          double* __restrict__ A4, uint8_t* __restrict__ nimg, uint8_t* __restrict__ flags) {
-    if (perm != nullptr && perm_close != nullptr && __ldg(perm_close) < perm_need) perm = nullptr;
     __shared__ cd s_roots[2][5][MLM_BLOCK];
     cd* const sz = &s_roots[0][0][threadIdx.x];
     cd* const szp = &s_roots[1][0][threadIdx.x];
@@ -110,7 +105,7 @@ k_points(const __grid_constant__ LensTable T, const SourceFactors sf, const doub
         cd zt = mk(0.0, 0.0), d = mk(0.0, 0.0);
         __syncwarp();
         if (act) {
-        i = perm ? (int64_t)__ldg(perm + iv) : iv;
+        i = iv;
         const double2 zz = __ldg(zeta + i);
         zt = mk(zz.x, zz.y);
         d = zt - zprev;
@@ -136,103 +131,6 @@ k_points(const __grid_constant__ LensTable T, const SourceFactors sf, const doub
             dprev = d;
         }
     }
-}
-
-// Unordered lists (mlm_points_unordered): bounding box, Hilbert-curve keys of the positions on a 65536 x 65536 grid
-// over the box, radix sort of (key, index) -- CUB, library plumbing -- and k_points along the sorted order.
-__device__ __forceinline__ unsigned long long dbl_ordered(double v) {      // order-preserving map double -> uint64
-    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
-    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
-}
-__device__ __forceinline__ double ordered_dbl(unsigned long long u) {
-    const unsigned long long b = (u & 0x8000000000000000ull) ? (u & 0x7fffffffffffffffull) : ~u;
-    return __longlong_as_double((long long)b);
-}
-
-// bbox[0..3] = ordered(min x), ordered(max x), ordered(min y), ordered(max y); non-finite coordinates are ignored
-__global__ void k_bbox(const double2* __restrict__ zeta, int64_t n, unsigned long long* __restrict__ bbox) {
-    unsigned long long lo_x = ~0ull, hi_x = 0ull, lo_y = ~0ull, hi_y = 0ull;
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
-        const double2 z = __ldg(zeta + i);
-        if (isfinite(z.x) && isfinite(z.y)) {
-            const unsigned long long ux = dbl_ordered(z.x), uy = dbl_ordered(z.y);
-            lo_x = ux < lo_x ? ux : lo_x; hi_x = ux > hi_x ? ux : hi_x;
-            lo_y = uy < lo_y ? uy : lo_y; hi_y = uy > hi_y ? uy : hi_y;
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        unsigned long long t;
-        t = __shfl_down_sync(0xffffffffu, lo_x, o); lo_x = t < lo_x ? t : lo_x;
-        t = __shfl_down_sync(0xffffffffu, hi_x, o); hi_x = t > hi_x ? t : hi_x;
-        t = __shfl_down_sync(0xffffffffu, lo_y, o); lo_y = t < lo_y ? t : lo_y;
-        t = __shfl_down_sync(0xffffffffu, hi_y, o); hi_y = t > hi_y ? t : hi_y;
-    }
-    // one set of atomics per block, not per warp (tens of thousands of atomics on four addresses serialise)
-    __shared__ unsigned long long sh[4][8];
-    const int w = threadIdx.x >> 5;
-    if ((threadIdx.x & 31) == 0) { sh[0][w] = lo_x; sh[1][w] = hi_x; sh[2][w] = lo_y; sh[3][w] = hi_y; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int k = 1; k < (int)(blockDim.x >> 5); ++k) {
-            lo_x = sh[0][k] < lo_x ? sh[0][k] : lo_x; hi_x = sh[1][k] > hi_x ? sh[1][k] : hi_x;
-            lo_y = sh[2][k] < lo_y ? sh[2][k] : lo_y; hi_y = sh[3][k] > hi_y ? sh[3][k] : hi_y;
-        }
-        atomicMin(bbox + 0, lo_x); atomicMax(bbox + 1, hi_x);
-        atomicMin(bbox + 2, lo_y); atomicMax(bbox + 3, hi_y);
-    }
-}
-
-// index of cell (x, y) of a 65536 x 65536 grid along the Hilbert curve: consecutive indices are ADJACENT cells (a
-// Morton / Z-order curve jumps across the grid at every quadrant boundary, and every jump of more than 0.02 Einstein
-// radii is a cold solve of one lane that the other 31 wait for)
-__device__ __forceinline__ uint32_t hilbert16(uint32_t x, uint32_t y) {
-    uint32_t d = 0;
-#pragma unroll
-    for (uint32_t s = 1u << 15; s > 0; s >>= 1) {
-        const uint32_t rx = (x & s) ? 1u : 0u, ry = (y & s) ? 1u : 0u;
-        d += s * s * ((3u * rx) ^ ry);
-        if (ry == 0) {
-            if (rx == 1) { x = 65535u - x; y = 65535u - y; }
-            const uint32_t t = x; x = y; y = t;
-        }
-    }
-    return d;
-}
-
-// every 8th consecutive pair of the sorted order: how many are within 0.01 Einstein radii of each other?
-__global__ void __launch_bounds__(256) k_perm_check(const double2* __restrict__ zeta, const uint32_t* __restrict__ perm,
-                                                    int64_t n, unsigned* __restrict__ close) {
-    const int64_t j = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 8;
-    unsigned c = 0;
-    if (j + 1 < n) {
-        const double2 a = __ldg(zeta + __ldg(perm + j)), b = __ldg(zeta + __ldg(perm + j + 1));
-        const double dx = b.x - a.x, dy = b.y - a.y;
-        c = (dx * dx + dy * dy <= 1e-4) ? 1u : 0u;
-    }
-    c = __reduce_add_sync(0xffffffffu, c);
-    if ((threadIdx.x & 31) == 0 && c) atomicAdd(close, c);
-}
-
-__global__ void __launch_bounds__(256) k_curve_keys(const double2* __restrict__ zeta, int64_t n,
-                                                const unsigned long long* __restrict__ bbox,
-                                                uint32_t* __restrict__ keys, uint32_t* __restrict__ idx) {
-    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (i >= n) return;
-    const double x_lo = ordered_dbl(bbox[0]), x_hi = ordered_dbl(bbox[1]);
-    const double y_lo = ordered_dbl(bbox[2]), y_hi = ordered_dbl(bbox[3]);
-    // one square cell size for both axes (distances matter, not the aspect ratio of the box)
-    const double ext = fmax(fmax(x_hi - x_lo, y_hi - y_lo), 1e-300);
-    const double sc = 65535.0 / ext;
-    const double2 z = __ldg(zeta + i);
-    uint32_t key = 0xffffffffu;                                           // non-finite entries last
-    if (isfinite(z.x) && isfinite(z.y)) {
-        const uint32_t cx = (uint32_t)fmin(fmax((z.x - x_lo) * sc, 0.0), 65535.0);
-        const uint32_t cy = (uint32_t)fmin(fmax((z.y - y_lo) * sc, 0.0), 65535.0);
-        key = hilbert16(cx, cy);
-    }
-    keys[i] = key;
-    idx[i] = (uint32_t)i;
 }
 
 // K1e: list of UNRELATED positions (mlm_points_unordered), one position per thread, nothing carried between entries --
@@ -825,7 +723,6 @@ struct mlm_context {
     // caller's stream and touch no context state.
     std::recursive_mutex mu;
     int anchor_segment = 16;                           // columns per thread of k_anchor (MLM_MAP_ANCHOR; 0: no anchors, cold strip starts)
-    int unordered_sorted = 0;                          // MLM_UNORDERED=sorted: mlm_points_unordered visits the list along a Hilbert curve (tracking) instead of solving every entry on its own
     int u8rows_env = -1;                               // MLM_MAP_U8ROWS = 0/1 forces the row-wise one-byte stores off/on (experiments)
     int points_segment = 0;                            // consecutive list entries per thread of k_points (0: from n; MLM_POINTS_SEGMENT)
     int models_segment = 0;                            // epochs per warm-start segment of k_models (0: from T; MLM_SEGMENT)
@@ -924,7 +821,6 @@ int mlm_create(int device, mlm_context** out) {
         if (v >= 1 && v <= 4096) ctx->map_strip_env = v;
     }
     if (const char* e6 = getenv("MLM_MAP_U8ROWS")) ctx->u8rows_env = atoi(e6) ? 1 : 0;
-    if (const char* e7 = getenv("MLM_UNORDERED")) ctx->unordered_sorted = (strcmp(e7, "sorted") == 0);
     if (const char* e5 = getenv("MLM_MAP_ANCHOR")) {
         const int v = atoi(e5);
         if (v >= 0 && v <= 4096) ctx->anchor_segment = v;
@@ -1115,9 +1011,9 @@ int mlm_points(mlm_context* ctx, double s, double q, double rho, double Gamma, c
     const unsigned blocks = (unsigned)((nthreads + MLM_BLOCK - 1) / MLM_BLOCK);
     cudaStream_t st = pick(ctx, stream);
     if (order == 4)
-        k_points<4><<<blocks, MLM_BLOCK, 0, st>>>(T, sf, (const double2*)zeta, n, seg, nullptr, nullptr, 0u, A0, A2, A4, nimg, flags);
+        k_points<4><<<blocks, MLM_BLOCK, 0, st>>>(T, sf, (const double2*)zeta, n, seg, A0, A2, A4, nimg, flags);
     else
-        k_points<2><<<blocks, MLM_BLOCK, 0, st>>>(T, sf, (const double2*)zeta, n, seg, nullptr, nullptr, 0u, A0, A2, A4, nimg, flags);
+        k_points<2><<<blocks, MLM_BLOCK, 0, st>>>(T, sf, (const double2*)zeta, n, seg, A0, A2, A4, nimg, flags);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -1133,79 +1029,26 @@ int mlm_points_unordered(mlm_context* ctx, double s, double q, double rho, doubl
     if (n < 4096) return mlm_points(ctx, s, q, rho, Gamma, zeta, n, order, A0, A2, A4, nimg, flags, stream);
     DeviceGuard g(ctx->device);
     cudaStream_t st = pick(ctx, stream);
-    if (!ctx->unordered_sorted) {
-        // every entry on its own: three-image guesses, then the root finder on the compacted rest
-        LensTable T;
-        make_table(s, q, &T);
-        const SourceFactors sf = source_factors(rho, Gamma);
-        char* ws = nullptr;
-        CK(cudaMallocAsync((void**)&ws, 256 + (size_t)n * sizeof(uint32_t), st));
-        unsigned* counter = (unsigned*)ws;
-        uint32_t* worklist = (uint32_t*)(ws + 256);
-        cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned), st);
-        if (e == cudaSuccess) {
-            const unsigned blocks = (unsigned)((n + MLM_BLOCK - 1) / MLM_BLOCK);
-            const unsigned blocks2 = blocks < (unsigned)ctx->sm_count * 8u ? blocks : (unsigned)ctx->sm_count * 8u;
-            if (order == 4) {
-                k_points_direct<4><<<blocks, MLM_BLOCK, 0, st>>>(T, sf, (const double2*)zeta, n, worklist, counter, A0, A2, A4, nimg, flags);
-                k_points_list<4><<<blocks2, MLM_BLOCK, 0, st>>>(T, sf, (const double2*)zeta, worklist, counter, A0, A2, A4, nimg, flags);
-            } else {
-                k_points_direct<2><<<blocks, MLM_BLOCK, 0, st>>>(T, sf, (const double2*)zeta, n, worklist, counter, A0, A2, A4, nimg, flags);
-                k_points_list<2><<<blocks2, MLM_BLOCK, 0, st>>>(T, sf, (const double2*)zeta, worklist, counter, A0, A2, A4, nimg, flags);
-            }
-            ctx->launches += 2;
-            e = cudaGetLastError();
+    // every entry on its own: three-image guesses, then the root finder on the compacted rest
+    LensTable T;
+    make_table(s, q, &T);
+    const SourceFactors sf = source_factors(rho, Gamma);
+    char* ws = nullptr;                                  // stream-ordered scratch: counter | work list
+    CK(cudaMallocAsync((void**)&ws, 256 + (size_t)n * sizeof(uint32_t), st));
+    unsigned* counter = (unsigned*)ws;
+    uint32_t* worklist = (uint32_t*)(ws + 256);
+    cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned), st);
+    if (e == cudaSuccess) {
+        const unsigned blocks = (unsigned)((n + MLM_BLOCK - 1) / MLM_BLOCK);
+        const unsigned blocks2 = blocks < (unsigned)ctx->sm_count * 8u ? blocks : (unsigned)ctx->sm_count * 8u;
+        if (order == 4) {
+            k_points_direct<4><<<blocks, MLM_BLOCK, 0, st>>>(T, sf, (const double2*)zeta, n, worklist, counter, A0, A2, A4, nimg, flags);
+            k_points_list<4><<<blocks2, MLM_BLOCK, 0, st>>>(T, sf, (const double2*)zeta, worklist, counter, A0, A2, A4, nimg, flags);
+        } else {
+            k_points_direct<2><<<blocks, MLM_BLOCK, 0, st>>>(T, sf, (const double2*)zeta, n, worklist, counter, A0, A2, A4, nimg, flags);
+            k_points_list<2><<<blocks2, MLM_BLOCK, 0, st>>>(T, sf, (const double2*)zeta, worklist, counter, A0, A2, A4, nimg, flags);
         }
-        cudaFreeAsync(ws, st);
-        if (e != cudaSuccess) return fail(ctx, (int)e, "mlm_points_unordered");
-        return 0;
-    }
-    // stream-ordered scratch: bbox | keys in/out | indices in/out | CUB temporary storage
-    size_t cub_bytes = 0;
-    CK(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
-                                       (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, 0, 32, st));
-    const size_t npad = ((size_t)n + 63) & ~(size_t)63;
-    char* ws = nullptr;
-    CK(cudaMallocAsync((void**)&ws, 256 + 4 * npad * sizeof(uint32_t) + cub_bytes, st));
-    unsigned long long* bbox = (unsigned long long*)ws;
-    uint32_t* keys = (uint32_t*)(ws + 256);
-    uint32_t* keys_out = keys + npad;
-    uint32_t* idx = keys_out + npad;
-    uint32_t* perm = idx + npad;
-    void* cub_ws = perm + npad;
-    unsigned* close = (unsigned*)(bbox + 4);
-    const unsigned long long init[5] = {~0ull, 0ull, ~0ull, 0ull, 0ull};
-    cudaError_t e = cudaMemcpyAsync(bbox, init, sizeof(init), cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) {
-        const unsigned nb = (unsigned)((n + 255) / 256);
-        k_bbox<<<nb < 592u ? nb : 592u, 256, 0, st>>>((const double2*)zeta, n, bbox);
-        k_curve_keys<<<nb, 256, 0, st>>>((const double2*)zeta, n, bbox, keys, idx);
         ctx->launches += 2;
-        e = cub::DeviceRadixSort::SortPairs(cub_ws, cub_bytes, keys, keys_out, idx, perm, (int)n, 0, 32, st);
-    }
-    const int64_t npairs = (n + 7) / 8;
-    if (e == cudaSuccess) {
-        k_perm_check<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>((const double2*)zeta, perm, n, close);
-        ctx->launches++;
-    }
-    if (e == cudaSuccess) {
-        LensTable T;
-        make_table(s, q, &T);
-        const SourceFactors sf = source_factors(rho, Gamma);
-        // runs of 16 sorted entries per thread: neighbours along the curve are tracked, a run start is a cold solve
-        // (all lanes of a warp together); shorter runs while the list is too small to fill the GPU with 16
-        const int64_t resident = (int64_t)ctx->sm_count * 4 * MLM_BLOCK;
-        int seg = ctx->points_segment > 0 ? ctx->points_segment : (int)((n + resident - 1) / resident);
-        if (ctx->points_segment <= 0) seg = seg < 4 ? 4 : (seg > 16 ? 16 : seg);
-        const int64_t nthreads = (n + seg - 1) / seg;
-        const unsigned blocks = (unsigned)((nthreads + MLM_BLOCK - 1) / MLM_BLOCK);
-        if (order == 4)
-            k_points<4><<<blocks, MLM_BLOCK, 0, st>>>(T, sf, (const double2*)zeta, n, seg, perm, close,
-                                                      (unsigned)(npairs * 9 / 10), A0, A2, A4, nimg, flags);
-        else
-            k_points<2><<<blocks, MLM_BLOCK, 0, st>>>(T, sf, (const double2*)zeta, n, seg, perm, close,
-                                                      (unsigned)(npairs * 9 / 10), A0, A2, A4, nimg, flags);
-        ctx->launches++;
         e = cudaGetLastError();
     }
     cudaFreeAsync(ws, st);
