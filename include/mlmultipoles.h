@@ -121,7 +121,7 @@ int mlm_points(mlm_context* ctx, double s, double q, double rho, double Gamma,
  * the other two roots of the quintic by Vieta; entries that this does not solve (inside and next to resonant caustics)
  * are compacted into a work list and solved by the root finder (Laguerre + deflation + polish) in a second launch.
  * Image counts equal mlm_points' cold solve, values to rounding; MLM_FLAG_EXTRA / MLM_FLAG_AMBIG report polynomial
- * rounding noise and agree with the root-finder path in distribution, not position by position.  n < 2^32.
+ * rounding noise and agree with the root-finder path in distribution, not position by position.  n < 2^31.
  * mlm_points_host checks a sample of the list for coherence and picks between the two. */
 int mlm_points_unordered(mlm_context* ctx, double s, double q, double rho, double Gamma,
                          const double* zeta, int64_t n, int order,

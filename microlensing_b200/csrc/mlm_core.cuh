@@ -264,6 +264,14 @@ MLM_HD void lens_polynomial_c045(const LensTable& T, cd zeta, cd& c0, cd& c4, cd
 #ifndef MLM_COUNT
 #define MLM_COUNT(name)                              /* test-only instrumentation hook */
 #endif
+// explicit reconvergence points of loops with lane-dependent trip counts (device only; no-ops in the host build)
+#if defined(__CUDA_ARCH__)
+#define MLM_ACTIVEMASK() __activemask()
+#define MLM_SYNCWARP(m) __syncwarp(m)
+#else
+#define MLM_ACTIVEMASK() 0u
+#define MLM_SYNCWARP(m) ((void)(m))
+#endif
 #define MLM_EPS 1.1102230246251565e-16               /* 2^-53 */
 #define MLM_LAG_MAXIT 64
 // Newton on the quintic stops once a step is below 1e-6 d, d = distance of the root to the nearer
@@ -986,15 +994,29 @@ MLM_HD cd point_lens_image(cd u, double m, double sign) {        // u (1 + sign 
     return scale(f, u);
 }
 
-MLM_HD bool guess_solve(const LensTable& T, cd zeta, cd* sz, int stride, int& extra, unsigned& flags) {
+// Returns MLM_GUESS_FAILED (the root finder has to solve the position), MLM_GUESS_THREE (exactly the three images: the
+// Vieta pair is nowhere near satisfying the lens equation -- no threshold, no rounding noise can change that) or
+// MLM_GUESS_CLASSIFY: the pair is within 0.1 of the lens equation (or not a number) and the five roots must go through
+// classify_roots.  With allow_classify the pair is polished on the quintic for that; without it the function returns
+// MLM_GUESS_CLASSIFY at once so that the caller can set such positions aside (k_points_direct: next to caustics they
+// are ~10 % of a light curve, i.e. some lane of almost every warp -- classifying them on the spot leaves 17 of 32
+// lanes active over the whole kernel).
+#define MLM_GUESS_FAILED 0
+#define MLM_GUESS_THREE 1
+#define MLM_GUESS_CLASSIFY 2
+MLM_HD int guess_solve(const LensTable& T, cd zeta, cd* sz, int stride, int& extra, unsigned& flags, bool allow_classify) {
     extra = 0;
-    cd c[6];
-    lens_polynomial(T, zeta, c);
-    if (c[5].x == 0.0 && c[5].y == 0.0) return false;
+    int status = MLM_GUESS_THREE;
+    // the lanes that enter together leave the Newton loops together: no early return before the loops, and an explicit
+    // reconvergence point after each (without it the lanes drift apart over the rest of the function -- measured on a
+    // shuffled light curve: 16.9 of 32 lanes active over the whole kernel instead of 25.5)
+    const unsigned entry_mask = MLM_ACTIVEMASK();
+    cd c0, c4, c5;
+    lens_polynomial_c045(T, zeta, c0, c4, c5);
     const double m1 = T.alpha[1], m2 = T.beta[1], is = rcp(T.s);
     cd sum = mk(0.0, 0.0);
-    double mag = 1.0;
-    bool ok = true;
+    double mag = 1.0, dmin2 = 1e300;
+    bool ok = !(c5.x == 0.0 && c5.y == 0.0);            // degenerate polynomial: the root finder's business
 #pragma unroll 1
     for (int k = 0; k < 3; ++k) {
         cd zk;
@@ -1002,10 +1024,10 @@ MLM_HD bool guess_solve(const LensTable& T, cd zeta, cd* sz, int stride, int& ex
         else if (k == 1) zk = mk(-T.s, 0.0) + point_lens_image(mk(zeta.x - m1 * is + T.s, zeta.y), m2, -1.0);
         else zk = mk(-T.s * m2, 0.0) + point_lens_image(mk(zeta.x + T.s * m2, zeta.y), 1.0, 1.0);
         bool conv = false;
-        double lim = 1e300;
+        double lim = 1e300, z2 = 0.0, zs2 = 0.0;
 #pragma unroll 1
         for (int it = 0; it < 10; ++it) {
-            double dz2, z2, zs2;
+            double dz2;
             const cd zn = lens_newton(T, zeta, zk, dz2, z2, zs2);
             MLM_COUNT(lens_evals);
             if (!(dz2 < lim)) break;
@@ -1017,55 +1039,73 @@ MLM_HD bool guess_solve(const LensTable& T, cd zeta, cd* sz, int stride, int& ex
         sz[k * stride] = zk;
         sum = sum + zk;
         mag += norm2(zk);
+        dmin2 = fmin(dmin2, fmin(z2, zs2));              // distances of the last evaluation: the step after it is < 1e-7 of them
+        MLM_SYNCWARP(entry_mask);
     }
-    if (!ok) return false;
+    if (!ok) return MLM_GUESS_FAILED;
     const cd z0 = sz[0], z1 = sz[stride], z2 = sz[2 * stride];
     const double tol = 1e-12 * mag;
-    if (!(norm2(z0 - z1) > tol && norm2(z0 - z2) > tol && norm2(z1 - z2) > tol)) return false;
+    if (!(norm2(z0 - z1) > tol && norm2(z0 - z2) > tol && norm2(z1 - z2) > tol)) return MLM_GUESS_FAILED;
     // the other two roots: r4 + r5 = S, r4 r5 = P
-    const cd ic5 = crcp(c[5]);
-    const cd S = -(cfma(c[4], ic5, sum));
-    const cd P = -(cmul(cmul(c[0], ic5), crcp(cmul(cmul(z0, z1), z2))));
+    const cd ic5 = crcp(c5);
+    const cd S = -(cfma(c4, ic5, sum));
+    const cd P = -(cmul(cmul(c0, ic5), crcp(cmul(cmul(z0, z1), z2))));
     cd sq = csqrt_(rfma(-4.0, P, csq(S)));
     if (re_mulc(S, sq) < 0.0) sq = -sq;
     cd r4 = scale(0.5, S + sq);
     cd r5 = cmul(P, crcp(r4));
-    if (!(quintic_newton(c, T.s, r4) && quintic_newton(c, T.s, r5))) return false;
-    // five distinct roots?  (Vieta on the polished pair)
-    const cd v = cfma(c[4], ic5, sum + r4 + r5);
-    if (!(norm2(v) <= 1e-16 * (mag + norm2(r4) + norm2(r5)))) return false;
-    sz[3 * stride] = r4;
-    sz[4 * stride] = r5;
-    // images next to a lens: would their polynomial root pass the plain test?
+    const bool near_lens = dmin2 < 1e-3;                 // an image with |W2| = m / d^2 > 1e3 m
+    const bool pair_near = !(lens_residual2(T, zeta, r4) >= 1e-2 && lens_residual2(T, zeta, r5) >= 1e-2);
+    if (pair_near && !allow_classify) return MLM_GUESS_CLASSIFY;
+    if (pair_near || near_lens) {
+        cd c[6];
+        lens_polynomial(T, zeta, c);
+        if (pair_near) {
+            status = MLM_GUESS_CLASSIFY;
+            if (!(quintic_newton(c, T.s, r4) && quintic_newton(c, T.s, r5))) return MLM_GUESS_FAILED;
+            // five distinct roots?  (Vieta on the polished pair)
+            const cd v = cfma(c4, ic5, sum + r4 + r5);
+            if (!(norm2(v) <= 1e-16 * (mag + norm2(r4) + norm2(r5)))) return MLM_GUESS_FAILED;
+        }
+        // images next to a lens: would their polynomial root pass the plain test?
 #pragma unroll 1
-    for (int k = 0; k < 3; ++k) {
-        const cd zk = sz[k * stride];
-        const double d2 = fmin(norm2(zk), norm2(mk(zk.x + T.s, zk.y)));
-        if (d2 < 1e-3) {                                 // |W2| = m / d^2 > 1e3 m
-            double dz2;
-            const cd zq = newton_step(c, zk, dz2);
-            const double f2 = lens_residual2(T, zeta, zq);
-            if (f2 > 1e-14 && f2 < 1e-10) flags |= MLM_FLAG_AMBIG;      // like classify_roots on a polynomial root
-            if (!(f2 < 1e-12)) ++extra;
+        for (int k = 0; k < 3; ++k) {
+            const cd zk = sz[k * stride];
+            const double d2 = fmin(norm2(zk), norm2(mk(zk.x + T.s, zk.y)));
+            if (d2 < 1e-3) {
+                double dz2;
+                const cd zq = newton_step(c, zk, dz2);
+                const double f2 = lens_residual2(T, zeta, zq);
+                if (f2 > 1e-14 && f2 < 1e-10) flags |= MLM_FLAG_AMBIG;      // like classify_roots on a polynomial root
+                if (!(f2 < 1e-12)) ++extra;
+            }
         }
     }
-    return true;
+    sz[3 * stride] = r4;
+    sz[4 * stride] = r5;
+    return status;
 }
 
-// whole path for one source position from the three-image guesses; false: not solved this way (nothing valid in out)
+// whole path for one source position from the three-image guesses.  Returns MLM_GUESS_THREE or MLM_GUESS_CLASSIFY when
+// `out` holds the result, MLM_GUESS_FAILED when the position is not solved this way, and -- without allow_classify --
+// MLM_GUESS_CLASSIFY with nothing valid in `out` for a position that needs the classification (see guess_solve).
 template <int ORDER>
-MLM_HD bool point_magnification_direct(const LensTable& T, const SourceFactors sf, cd zeta, cd* sz, int stride,
-                                       PointResult& out) {
-    int extra_g = 0, extra_c = 0;
+MLM_HD int point_magnification_direct(const LensTable& T, const SourceFactors sf, cd zeta, cd* sz, int stride,
+                                      PointResult& out, bool allow_classify = true) {
+    int extra = 0, nimg = 3;
     out.flags = 0;
-    if (!guess_solve(T, zeta, sz, stride, extra_g, out.flags)) return false;
-    MLM_COUNT(classify_calls);
-    const int nimg = classify_roots(T, zeta, sz, stride, out.flags, extra_c);
-    if (nimg < 3) return false;                          // cannot happen with three converged images; be safe
-    const int extra = extra_g + extra_c;
+    const int status = guess_solve(T, zeta, sz, stride, extra, out.flags, allow_classify);
+    if (status == MLM_GUESS_FAILED || (status == MLM_GUESS_CLASSIFY && !allow_classify)) return status;
+    if (status == MLM_GUESS_CLASSIFY) {
+        int extra_c = 0;
+        MLM_COUNT(classify_calls);
+        nimg = classify_roots(T, zeta, sz, stride, out.flags, extra_c);
+        if (nimg < 3) return MLM_GUESS_FAILED;           // cannot happen with three converged images; be safe
+        extra += extra_c;
+    }
     if (extra) out.flags |= MLM_FLAG_EXTRA | ((unsigned)(extra < 3 ? extra : 3) << MLM_FLAG_EXTRA_SHIFT);
     sum_images<ORDER>(T, sf, sz, stride, nimg, out);
-    return true;
+    return status;
 }
 
 // whole path for one source position (cold start)

@@ -136,61 +136,74 @@ k_points(const __grid_constant__ LensTable T, const SourceFactors sf, const doub
 // K1e: list of UNRELATED positions (mlm_points_unordered), one position per thread, nothing carried between entries --
 // the result of an entry does not depend on the rest of the list.  First pass (k_points_direct): the three images that
 // every binary-lens configuration has, by Newton on the lens equation from single-lens guesses, the other two roots of
-// the quintic by Vieta (point_magnification_direct, ~1 500 FP64 instructions with the sums).  Entries that this does
-// not solve (inside and next to resonant caustics, ~1 % of a planetary light curve, half of a map window centred on a
-// resonant caustic) are appended to a work list -- one atomicAdd per warp -- instead of being solved on the spot with
-// 31 lanes waiting, and the second pass (k_points_list) runs the root finder (Laguerre + deflation + polish,
-// ~4 600 warp-level instructions per entry) on the COMPACTED list with full warps.
+// the quintic by Vieta (point_magnification_direct, ~1 300 FP64 instructions with the sums).  What this does not
+// finish is set aside -- one atomicAdd per warp and list -- instead of being dealt with on the spot with most lanes
+// waiting, and two more launches work through the COMPACTED lists with full warps:
+//   list 1 (k_points_list<ORDER, 1>): three images found, but the other two roots are close to the lens equation and
+//           need the classification (next to caustics: ~10 % of a planetary light curve);
+//   list 0 (k_points_list<ORDER, 0>): the guesses did not converge on three distinct images (inside and next to
+//           resonant caustics: ~1 % of a planetary light curve, half of a map window centred on a resonant caustic):
+//           root finder (Laguerre + deflation + polish, ~4 600 warp-level instructions per entry).
+// lists[0 .. n) is list 0, lists[n .. 2n) list 1; counters[0], counters[1] their lengths.
 template <int ORDER>
 __global__ void __launch_bounds__(MLM_BLOCK, 4)
 k_points_direct(const __grid_constant__ LensTable T, const SourceFactors sf, const double2* __restrict__ zeta, int64_t n,
-                uint32_t* __restrict__ worklist, unsigned* __restrict__ counter, double* __restrict__ A0,
+                uint32_t* __restrict__ lists, unsigned* __restrict__ counters, double* __restrict__ A0,
                 double* __restrict__ A2, double* __restrict__ A4, uint8_t* __restrict__ nimg, uint8_t* __restrict__ flags) {
     __shared__ cd s_roots[5][MLM_BLOCK];
     cd* const sz = &s_roots[0][threadIdx.x];
     const int64_t i = (int64_t)blockIdx.x * MLM_BLOCK + threadIdx.x;
     const bool act = i < n;
-    bool solved = true;
+    int status = MLM_GUESS_THREE;
     PointResult r;
     r.flags = 0;
     if (act) {
         const double2 zz = __ldg(zeta + i);
         MLM_COUNT(positions);
-        solved = point_magnification_direct<ORDER>(T, sf, mk(zz.x, zz.y), sz, MLM_BLOCK, r);
-        if (solved) store_result(r, i, A0, A2, A4, nimg, flags);
+        status = point_magnification_direct<ORDER>(T, sf, mk(zz.x, zz.y), sz, MLM_BLOCK, r, false);
+        if (status == MLM_GUESS_THREE) store_result(r, i, A0, A2, A4, nimg, flags);
     }
     __syncwarp();
-    const unsigned fail = __ballot_sync(0xffffffffu, !solved);
-    if (fail) {
-        const int lane = threadIdx.x & 31;
-        unsigned base = 0;
-        if (lane == 0) base = atomicAdd(counter, (unsigned)__popc(fail));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (!solved) worklist[base + __popc(fail & ((1u << lane) - 1u))] = (uint32_t)i;
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int l = 0; l < 2; ++l) {
+        const bool mine = status == (l ? MLM_GUESS_CLASSIFY : MLM_GUESS_FAILED);
+        const unsigned m = __ballot_sync(0xffffffffu, mine);
+        if (m) {
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(counters + l, (unsigned)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (mine) lists[(size_t)l * (size_t)n + base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)i;
+        }
     }
 }
 
-template <int ORDER>
+template <int ORDER, int MODE>
 __global__ void __launch_bounds__(MLM_BLOCK, 4)
-k_points_list(const __grid_constant__ LensTable T, const SourceFactors sf, const double2* __restrict__ zeta,
-              const uint32_t* __restrict__ worklist, const unsigned* __restrict__ counter, double* __restrict__ A0,
+k_points_list(const __grid_constant__ LensTable T, const SourceFactors sf, const double2* __restrict__ zeta, int64_t n,
+              const uint32_t* __restrict__ lists, const unsigned* __restrict__ counters, double* __restrict__ A0,
               double* __restrict__ A2, double* __restrict__ A4, uint8_t* __restrict__ nimg, uint8_t* __restrict__ flags) {
     __shared__ cd s_roots[5][MLM_BLOCK];
     cd* const sz = &s_roots[0][threadIdx.x];
-    const unsigned cnt = __ldg(counter);
+    const unsigned cnt = __ldg(counters + MODE);
+    const uint32_t* const list = lists + (size_t)MODE * (size_t)n;
     for (unsigned j0 = blockIdx.x * MLM_BLOCK; j0 < cnt; j0 += gridDim.x * MLM_BLOCK) {
         const unsigned j = j0 + threadIdx.x;
         __syncwarp();
         if (j >= cnt) continue;
-        const int64_t i = (int64_t)__ldg(worklist + j);
+        const int64_t i = (int64_t)__ldg(list + j);
         const double2 zz = __ldg(zeta + i);
+        const cd zt = mk(zz.x, zz.y);
         PointResult r;
         r.flags = 0;
-        TrackState st;
-        st.hist = 0; st.nimg = 0; st.extra = 0;
         MLM_COUNT(positions);
-        advance_images(T, mk(zz.x, zz.y), sz, sz, nullptr, MLM_BLOCK, st, r.flags);
-        sum_images<ORDER>(T, sf, sz, MLM_BLOCK, st.nimg, r);
+        if (MODE == 0 || point_magnification_direct<ORDER>(T, sf, zt, sz, MLM_BLOCK, r, true) == MLM_GUESS_FAILED) {
+            r.flags = 0;
+            TrackState st;
+            st.hist = 0; st.nimg = 0; st.extra = 0;
+            advance_images(T, zt, sz, sz, nullptr, MLM_BLOCK, st, r.flags);
+            sum_images<ORDER>(T, sf, sz, MLM_BLOCK, st.nimg, r);
+        }
         store_result(r, i, A0, A2, A4, nimg, flags);
     }
 }
@@ -1022,7 +1035,7 @@ int mlm_points(mlm_context* ctx, double s, double q, double rho, double Gamma, c
 int mlm_points_unordered(mlm_context* ctx, double s, double q, double rho, double Gamma, const double* zeta, int64_t n,
                          int order, double* A0, double* A2, double* A4, uint8_t* nimg, uint8_t* flags, void* stream) {
     if (!ctx) return fail(ctx, MLM_EINVAL, "mlm_points_unordered: NULL context");
-    if (n < 0 || n > 0xffffffffll || (order != 2 && order != 4) || bad_lens(s, q))
+    if (n < 0 || n > 0x7fffffffll || (order != 2 && order != 4) || bad_lens(s, q))
         return fail(ctx, MLM_EINVAL, "mlm_points_unordered: bad argument");
     if (n == 0) return 0;
     if (!zeta || !(A0 || A2 || A4 || nimg || flags)) return fail(ctx, MLM_EINVAL, "mlm_points_unordered: NULL buffer");
@@ -1033,22 +1046,25 @@ int mlm_points_unordered(mlm_context* ctx, double s, double q, double rho, doubl
     LensTable T;
     make_table(s, q, &T);
     const SourceFactors sf = source_factors(rho, Gamma);
-    char* ws = nullptr;                                  // stream-ordered scratch: counter | work list
-    CK(cudaMallocAsync((void**)&ws, 256 + (size_t)n * sizeof(uint32_t), st));
-    unsigned* counter = (unsigned*)ws;
-    uint32_t* worklist = (uint32_t*)(ws + 256);
-    cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned), st);
+    char* ws = nullptr;                                  // stream-ordered scratch: two counters | two work lists
+    CK(cudaMallocAsync((void**)&ws, 256 + 2 * (size_t)n * sizeof(uint32_t), st));
+    unsigned* counters = (unsigned*)ws;
+    uint32_t* lists = (uint32_t*)(ws + 256);
+    cudaError_t e = cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned), st);
     if (e == cudaSuccess) {
         const unsigned blocks = (unsigned)((n + MLM_BLOCK - 1) / MLM_BLOCK);
         const unsigned blocks2 = blocks < (unsigned)ctx->sm_count * 8u ? blocks : (unsigned)ctx->sm_count * 8u;
+        const double2* z2 = (const double2*)zeta;
         if (order == 4) {
-            k_points_direct<4><<<blocks, MLM_BLOCK, 0, st>>>(T, sf, (const double2*)zeta, n, worklist, counter, A0, A2, A4, nimg, flags);
-            k_points_list<4><<<blocks2, MLM_BLOCK, 0, st>>>(T, sf, (const double2*)zeta, worklist, counter, A0, A2, A4, nimg, flags);
+            k_points_direct<4><<<blocks, MLM_BLOCK, 0, st>>>(T, sf, z2, n, lists, counters, A0, A2, A4, nimg, flags);
+            k_points_list<4, 1><<<blocks2, MLM_BLOCK, 0, st>>>(T, sf, z2, n, lists, counters, A0, A2, A4, nimg, flags);
+            k_points_list<4, 0><<<blocks2, MLM_BLOCK, 0, st>>>(T, sf, z2, n, lists, counters, A0, A2, A4, nimg, flags);
         } else {
-            k_points_direct<2><<<blocks, MLM_BLOCK, 0, st>>>(T, sf, (const double2*)zeta, n, worklist, counter, A0, A2, A4, nimg, flags);
-            k_points_list<2><<<blocks2, MLM_BLOCK, 0, st>>>(T, sf, (const double2*)zeta, worklist, counter, A0, A2, A4, nimg, flags);
+            k_points_direct<2><<<blocks, MLM_BLOCK, 0, st>>>(T, sf, z2, n, lists, counters, A0, A2, A4, nimg, flags);
+            k_points_list<2, 1><<<blocks2, MLM_BLOCK, 0, st>>>(T, sf, z2, n, lists, counters, A0, A2, A4, nimg, flags);
+            k_points_list<2, 0><<<blocks2, MLM_BLOCK, 0, st>>>(T, sf, z2, n, lists, counters, A0, A2, A4, nimg, flags);
         }
-        ctx->launches += 2;
+        ctx->launches += 3;
         e = cudaGetLastError();
     }
     cudaFreeAsync(ws, st);

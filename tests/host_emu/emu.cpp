@@ -37,7 +37,7 @@ void emu_points(double s, double q, double rho, double Gamma, const double* zeta
 }
 
 // the same through the three-image guesses (k_points_direct), falling back to the root finder like the kernels do;
-// used[i] = 1 where the guesses solved the position
+// used[i] = MLM_GUESS_THREE / MLM_GUESS_CLASSIFY where the guesses solved the position, 0 where the root finder did
 void emu_points_direct(double s, double q, double rho, double Gamma, const double* zeta, long n, int order,
                        double* A0, double* A2, double* A4, unsigned char* nimg, unsigned char* flags, unsigned char* used) {
     LensTable T;
@@ -47,8 +47,11 @@ void emu_points_direct(double s, double q, double rho, double Gamma, const doubl
         cd z = mk(zeta[2 * i], zeta[2 * i + 1]);
         cd store[5];
         PointResult r;
-        bool ok = (order >= 4) ? point_magnification_direct<4>(T, sf, z, store, 1, r) : point_magnification_direct<2>(T, sf, z, store, 1, r);
-        used[i] = ok ? 1 : 0;
+        // k_points_direct sets positions that need the classification aside and k_points_list<.., 1> solves them with
+        // allow_classify: the same arithmetic as allowing it at once
+        const int st = (order >= 4) ? point_magnification_direct<4>(T, sf, z, store, 1, r) : point_magnification_direct<2>(T, sf, z, store, 1, r);
+        const bool ok = st != MLM_GUESS_FAILED;
+        used[i] = (unsigned char)st;
         if (!ok) r = (order >= 4) ? point_magnification<4>(T, sf, z) : point_magnification<2>(T, sf, z);
         A0[i] = r.A0; A2[i] = r.A2; A4[i] = r.A4;
         nimg[i] = (unsigned char)r.nimg; flags[i] = (unsigned char)r.flags;

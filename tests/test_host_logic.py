@@ -222,7 +222,7 @@ def test_logic_direct_cold_start_equals_root_finder(emu, golden_points):
         if ok.any():
             assert np.nanmax(np.abs(A1[ok] / A0[ok] - 1)) < 1e-9, p
         for t in np.unique(g["tags"][idx]):
-            solved.setdefault(str(t), []).append(used[g["tags"][idx] == t])
+            solved.setdefault(str(t), []).append(used[g["tags"][idx] == t] != 0)
     frac = {t: float(np.concatenate(v).mean()) for t, v in solved.items()}
     assert frac["C2"] > 0.9 and frac["C5"] > 0.8, frac
     rng = np.random.default_rng(17)

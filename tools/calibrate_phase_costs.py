@@ -16,6 +16,7 @@ PHASE_EVENT = {
     "cold_glue": "positions",
     "lens_newton": "lens_evals", "track_image_newton": "lens_evals",
     "track_nonphys_newton": "newton_evals", "track_nonphys_check": "nonphys_checks",
+    "track_quadratic": "quadratics", "watch_fp32": "quadratics", "track_polish": "watch_near",
     "cold_solve": "cold_solves", "classify": "classify_calls",
     "image_wk": "images", "image_terms": "images", "image_sums": "images",
 }

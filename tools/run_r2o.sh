@@ -1,0 +1,2 @@
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python tools/time_unordered.py

@@ -39,7 +39,7 @@ def run(name, s, q, zeta, rho=1e-3):
         rel = np.abs(A / B - 1).max(axis=1)
     w = rel[ok].max() if ok.any() else 0.0
     extra_d = ((fl >> 6) & 3).astype(int); extra_0 = ((f0 >> 6) & 3).astype(int)
-    print(f"{name}: N={zeta.size} solved by guesses {used.mean():.4f}  nimg mismatch {bad.sum()}  flag differences {fdiff.sum()} "
+    print(f"{name}: N={zeta.size} solved by guesses {(used != 0).mean():.4f} (with classification {(used == 2).mean():.4f})  nimg mismatch {bad.sum()}  flag differences {fdiff.sum()} "
           f"(EXTRA count differs {np.sum(extra_d != extra_0)})  max rel unflagged {w:.2e}  lens evals/pt {st[2] / zeta.size:.2f} lag/pt {st[0] / zeta.size:.2f}")
     if bad.any():
         i = np.where(bad)[0][:5]
