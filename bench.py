@@ -111,7 +111,7 @@ def sample_positions(cfg, n, seed=12345):
     raise ValueError(cfg["kind"])
 
 
-def run_cpu_baseline(cfg, per_core=6000, cores=None):
+def run_cpu_baseline(cfg, per_core=20000, cores=None):
     """Time the oracle's per-position replay on `cores` processes; returns dict + sample results."""
     import multiprocessing as mp
     cores = cores or os.cpu_count() or 1
@@ -993,8 +993,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the e2e legs (0: --steps)")
     ap.add_argument("--no-other", action="store_true", help="skip the other configurations (C2/C3/C5 timings and parity)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline and the parity blocks (profiling runs)")
-    ap.add_argument("--cpu-per-core", type=int, default=6000)
-    ap.add_argument("--ref-per-core", type=int, default=6000)
+    ap.add_argument("--cpu-per-core", type=int, default=20000)
+    ap.add_argument("--ref-per-core", type=int, default=20000)
     args = ap.parse_args()
     if args.impl == "reference":
         return bench_reference(args)

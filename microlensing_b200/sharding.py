@@ -109,22 +109,23 @@ def full_map_layout(nx: int, ny: int) -> tuple[dict, int]:
 MAX_SEL = 32                      # MLM_DEAL_MAXSEL of the C ABI: positions one rank may own in a round
 
 
-def root_share_model(world: int, bytes_per_position: float, rate: float = 9.6e9, ingress: float = 657e9,
+def root_share_model(world: int, bytes_per_position: float, rate: float = 1.17e10, ingress: float = 720e9,
                      latency_fraction: float = 0.0) -> float:
     """Share of the map the gather root should compute itself.
 
     Time of the root = f / rate per position; time for the peers' results to enter the root = (1 - f) x bytes /
     ingress; the peers compute (1 - f) / (world - 1) each.  The balanced share equalises the first two (never below
     the equal share 1 / world, never so large that the peers idle while the root still computes).
-    rate = positions/s of one GPU on this map in the 16-row strips of a sharded run (9.6e9 on the C4 map; 1.1e10 in
-    64-row strips), ingress = bytes/s into one GPU (measured: 657 GB/s for the map kernel's peer stores, 790 GB/s for
-    bulk peer copies; profiles/r2_ceilings_n8.json, profiles/r2b_gather_sweep.md).  A balanced share less than 15 %
+    rate = positions/s of one GPU on this map in the 16-row strips of a sharded run (1.17e10 on the C4 map; 1.2e10 in
+    64-row strips), ingress = bytes/s into one GPU (measured: ~720 GB/s for the map kernel's peer stores with the
+    one-byte arrays written 128 bytes at a time, 657 GB/s before that, 790 GB/s for bulk peer copies;
+    profiles/r2_ceilings_n8.json, profiles/r2b_gather_sweep.md; measured optimum at 8 GPUs: 3 of every 10 strips).  A balanced share less than 20 %
     above the equal one is not worth the coarser deal (measured at 4 GPUs): the equal share is returned."""
     if world <= 1:
         return 1.0
     a, b = 1.0 / rate, bytes_per_position / ingress
     f = (b * (1.0 + latency_fraction)) / (a + b)
-    if f < 1.15 / world:
+    if f < 1.2 / world:
         return 1.0 / world
     return min(f, 0.9)
 
@@ -192,7 +193,7 @@ class ShardedMap:
 
     def __init__(self, nx: int, ny: int, rank: int = 0, world: int = 1, device=None, nchunks: int | None = None,
                  group=None, align: int | None = None, gather: str | None = None, compute_fn=None,
-                 outputs=None, layout: str | None = None, root_share: float | None = None, rate_hint: float = 9.6e9):
+                 outputs=None, layout: str | None = None, root_share: float | None = None, rate_hint: float = 1.17e10):
         import torch
         self.torch = torch
         self.nx, self.ny = nx, ny
@@ -225,7 +226,7 @@ class ShardedMap:
         self.bytes_per_position = sum(item for k, item in KEYS if k in self.outputs)
         if layout == "weighted" and root_share is None:
             root_share = root_share_model(world, self.bytes_per_position, rate=rate_hint,
-                                          ingress=780e9 if gather == "bulk" else 657e9,
+                                          ingress=780e9 if gather == "bulk" else 720e9,
                                           latency_fraction=0.12 if gather == "bulk" else 0.0)
         self.root_share = root_share if layout == "weighted" else (1.0 / world)
         self.period, self.sel_all = deal_rounds(world, self.root_share if layout == "weighted" else None)
