@@ -371,7 +371,8 @@ def measure_executed(local, cfg, strip):
     return {"fp64_inst_per_mag": inst, "flop_per_mag": flop, "phases": phases, "positions_counted": npos,
             "calibration": {"file": "profiles/k_map_phase_costs.json", "source_hash": cal.get("source_hash"),
                             "ncu_fp64_inst_per_position": cal.get("ncu_fp64_inst_per_position"),
-                            "ncu_fp64_pipe_pct": cal.get("ncu_fp64_pipe_pct"), "profile": cal.get("profile")},
+                            "ncu_fp64_pipe_pct": cal.get("ncu_fp64_pipe_pct"), "profile": cal.get("profile"),
+                            "dram_bytes_per_launch": cal.get("dram_bytes_per_launch")},
             "source_hash_now": cur, "stale": cur != cal.get("source_hash"),
             "avg_active_lanes_fp64": cal.get("avg_active_lanes_fp64"),
             "source": "event counters of libmlmultipoles_stats.so (-DMLM_STATS) on this run's workload x FP64 thread "
@@ -659,6 +660,10 @@ def bench_b200(args):
                                            "nominal + the 20-factor a_kl recursion) x the measured rate; the kernel reaches the same "
                                            "numbers with several times less arithmetic (root/image tracking, closed operator form), so "
                                            "this is not a machine fraction"},
+        "limiter": "register-file operand bandwidth of the FP64 pipe: a DFMA with three distinct register operands issues "
+                   "every 3 cycles, not 2 (measured: operand_limited_issue_rate), and every other instruction (the FP32 "
+                   "watch, addressing, selects) takes read slots too -- frac counts FP64 flop only, "
+                   "frac_of_operand_limited_rate is the machine view (DESIGN.md §5)",
         "positions_per_launch": max_share * n_total, "kernel_ms_per_step": ms_kernel, "algorithmic_bytes_per_mag": 26,
         "launch": "the rank with the largest share of the strips (rank 0 of a weighted deal)" if world > 1 else "the whole map",
         "hbm_frac": (launch_rate * 26 / 1e9) / _hbm_peak(),

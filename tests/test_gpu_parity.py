@@ -11,6 +11,7 @@ import pytest
 
 import parity
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
 
@@ -43,7 +44,7 @@ def test_example_prints_reference_values(mb):
     with contextlib.redirect_stdout(buf):
         assert mb.multipoles.example() is None
     got = buf.getvalue().splitlines()
-    ref = open("tests/golden/example_stdout.txt").read().splitlines()
+    ref = open(os.path.join(ROOT, "tests", "golden", "example_stdout.txt")).read().splitlines()
     assert len(got) == 4 and got[1] == ref[1] and got[3] == ref[3]
     assert got[0].startswith(" A0, A2 =  ") and got[2].startswith(" A0, A2, A4 =  ")
     for a, b in ((got[0], ref[0]), (got[2], ref[2])):
