@@ -690,9 +690,15 @@ class ShardedModels:
                           for key, item in KEYS if key in self.outputs}
             with torch.cuda.device(self.device):
                 self.comm_stream = torch.cuda.Stream()
-        # pipelining units of the bulk copies: a chunk should still be a few waves of blocks (one block
-        # = one model; ~1000 resident blocks per GPU), small launches pay a start-up/drain phase each
-        self.nchunks = max(1, min(4, (self.hi - self.lo) // 1000))
+        # pipelining units of the bulk copies: a chunk must still be several ROUNDS of resident blocks (a block = 64
+        # segments of one light curve, 8 blocks resident per SM), or the tail of every chunk costs more than the
+        # overlap gains: 1250-model chunks of the C5 grid are 1.06 rounds and ran the 2-GPU job in 2.9 ms, one launch
+        # of 5000 models + one copy in ~1.6 ms
+        nseg = -(-self.T // max(self.segment, 1))
+        blocks = (self.hi - self.lo) * -(-nseg // 64)
+        resident = 8 * (torch.cuda.get_device_properties(self.device).multi_processor_count
+                        if self.device.type == "cuda" else 148)
+        self.nchunks = max(1, min(4, blocks // (4 * resident)))
 
     def compute(self, order=4):
         """Enqueue this rank's models on the current stream (results land in rank 0's buffer)."""
