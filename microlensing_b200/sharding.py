@@ -616,8 +616,8 @@ class ShardedModels:
     fit=(flux, sigma): the light-curve fit is fused into the kernel (mlm_models_chi2); only 8 doubles per
                model travel.
     A model's light curve does not depend on which rank computes it: the segment length of the kernel (`segment`,
-    default mlm_auto_segment of the WHOLE grid) is the same on every rank, so the result is bit-identical to the
-    single-GPU one computed with that segment.
+    default mlm_auto_segment of the LARGEST share of the grid, like the strip length of a sharded map) is the same on
+    every rank, so the result is bit-identical to the single-GPU one computed with that segment (`self.segment`).
     """
 
     STAT_KEYS = ("chi2", "Fs", "Fb", "SA", "SAA", "SAF", "n5", "nflag")
@@ -644,8 +644,9 @@ class ShardedModels:
         self.M = arrs[0].size
         self.lo, self.hi = shard_range(self.M, rank, world)
         self.par = [torch.from_numpy(a[self.lo:self.hi].copy()).to(self.device) for a in arrs]
-        # epochs per tracking segment: from the WHOLE grid, the same on every rank (the bits of a light curve depend on it)
-        self.segment = int(segment) if segment else _capi.context(self.device.index).auto_segment(self.M, self.T)
+        # epochs per tracking segment: the same on every rank (the bits of a light curve depend on it), chosen for the size
+        # of ONE rank's launch (a 1/8 share in the whole grid's 32-epoch segments is 1.06 rounds of resident blocks)
+        self.segment = int(segment) if segment else _capi.context(self.device.index).auto_segment(-(-self.M // world), self.T)
         self.outputs = tuple(k for k, _ in KEYS) if outputs is None else tuple(outputs)
         self.fit = None
         ctx = _capi.context(self.device.index)
