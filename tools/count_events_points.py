@@ -1,5 +1,5 @@
-"""Event counters (counting build) of k_points on the C2 light curve: ordered, shuffled (plain: cold each), shuffled
-through the sorted path, and random 2-D positions through both paths."""
+"""Event counters (counting build) of the point-list kernels on the C2 light curve: ordered, shuffled through the tracking
+kernel (a cold solve per entry), shuffled through mlm_points_unordered (direct path), and random 2-D positions through both."""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -16,8 +16,8 @@ b = [torch.empty(T, dtype=torch.float64, device=dev) for _ in range(3)] + [torch
 sctx = _capi.context(0, stats=True)
 st = torch.cuda.current_stream().cuda_stream
 out = {}
-for name, z, fn in (("ordered", zh, "mlm_points"), ("shuffled_plain", zs, "mlm_points"), ("shuffled_sorted", zs, "mlm_points_unordered"),
-                    ("random_plain", zr, "mlm_points"), ("random_sorted", zr, "mlm_points_unordered")):
+for name, z, fn in (("ordered", zh, "mlm_points"), ("shuffled_plain", zs, "mlm_points"), ("shuffled_unordered", zs, "mlm_points_unordered"),
+                    ("random_plain", zr, "mlm_points"), ("random_unordered", zr, "mlm_points_unordered")):
     zt = torch.from_numpy(z).to(dev)
     sctx.stats_read(reset=True)
     sctx.check(getattr(sctx.lib, fn)(sctx.handle, c["s"], c["q"], c["rho"], c["Gamma"], _capi.ptr(zt), T, 4, *[_capi.ptr(t) for t in b], _capi.ptr(st)), fn)
