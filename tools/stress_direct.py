@@ -47,7 +47,34 @@ def run(name, s, q, zeta, rho=1e-3):
     return bad.sum()
 
 
+def parity_accounting():
+    """Rule 5 of tests/parity.py (count disputes with the reference flagged EXTRA or reference-side ambiguous) for the direct path
+    and the root-finder path on the same random positions at small q: the two paths account for the disputes alike."""
+    sys.path.insert(0, _ROOT + '/tests')
+    import parity
+    from oracle import cassan_oracle as o
+    from oracle.truth_mp import truth_point
+    ce.lib = libs
+    rng = np.random.default_rng(3)
+    for s, q in ((1.013, 8.81e-5), (1.46, 3.86e-5), (0.863, 1.91e-4), (1.0, 1e-3), (1.2, 1e-5), (0.9, 3e-4)):
+        z = rng.uniform(-2, 2, 6000) + 1j * rng.uniform(-2, 2, 6000)
+        ni, A, fl, used = direct(s, q, 1e-3, 0.5, z)
+        n0, B0, B2, B4, f0 = ce.emu_points(s, q, 1e-3, 0.5, z)
+        nb, R0, R2, R4, zz, keep, minJ, res = o.batch_a4(s, q, 1e-3, 0.5, z, return_extra=True)
+        ref_A = np.stack([R0, R2, R4], 1)
+        mask = parity.mask_from_reference(ref_A, res, minJ)
+        for name, (gn, gA, gf) in (('direct', (ni, A, fl)), ('root finder', (n0, np.stack([B0, B2, B4], 1), f0))):
+            rep = parity.compare(gn, gA, nb, ref_A, mask, truth_fn=lambda i: truth_point(s, q, 1e-3, 0.5, z[i]), got_flags=gf,
+                                 strict=False, max_adjudicate=20)
+            print(f"s={s} q={q:.1e} {name:11s}: AMBIG {((gf & 8) != 0).mean():.3f}  count disputes {rep['nimg_mismatch']}  flagged EXTRA "
+                  f"{rep.get('nimg_mismatch_flagged_extra')}  reference-side ambiguous {rep.get('nimg_mismatch_ref_ambiguous')}  unaccounted "
+                  f"{rep.get('nimg_mismatch_unaccounted')}  adjudication failures {len(rep['adjudication_failures'])}")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "--parity":
+        parity_accounting()
+        sys.exit(0)
     rng = np.random.default_rng(11)
     N = 100000
     s, q = 1.0, 1e-3; tau = rng.uniform(-2, 2, N); run('C2', s, q, (tau + 0.01j) * np.exp(0.35j) - s * q / (1 + q))
