@@ -119,13 +119,16 @@ def root_share_model(world: int, bytes_per_position: float, rate: float = 1.17e1
     rate = positions/s of one GPU on this map in the 16-row strips of a sharded run (1.17e10 on the C4 map; 1.2e10 in
     64-row strips), ingress = bytes/s into one GPU (measured: ~720 GB/s for the map kernel's peer stores with the
     one-byte arrays written 128 bytes at a time, 657 GB/s before that, 790 GB/s for bulk peer copies;
-    profiles/r2_ceilings_n8.json, profiles/r2b_gather_sweep.md; measured optimum at 8 GPUs: 3 of every 10 strips).  A balanced share less than 20 %
-    above the equal one is not worth the coarser deal (measured at 4 GPUs): the equal share is returned."""
+    profiles/r2_ceilings_n8.json, profiles/r2b_gather_sweep.md; measured optimum at 8 GPUs: 3 of every 10 strips, at 4 GPUs
+    4 of every 13 -- 2.00 ms per C4 map against 2.16 ms with the equal deal and 2.05 ms with 3 of 9, tools/gpu_runs/run_r4b.sh).
+    The coarser deal has to pay: the balanced share is returned when the model predicts a step at least 5 % shorter than
+    with the equal deal (max of the root's compute and its peers' bytes), else the equal share."""
     if world <= 1:
         return 1.0
     a, b = 1.0 / rate, bytes_per_position / ingress
     f = (b * (1.0 + latency_fraction)) / (a + b)
-    if f < 1.2 / world:
+    t_equal = max(a / world, (1.0 - 1.0 / world) * b)
+    if f <= 1.0 / world or t_equal < 1.05 * a * f:
         return 1.0 / world
     return min(f, 0.9)
 

@@ -432,7 +432,8 @@ def test_weighted_deal_covers_every_strip_once(built):
         assert sorted(k for r in range(world) for k in owned_strips(8192, 16, period, sel[r])) == list(range(512))
     # the share model: equal shares while the gather is cheap, a larger root share once NVLink ingress binds
     assert root_share_model(2, 26) == 0.5 and root_share_model(1, 26) == 1.0
-    assert 0.28 < root_share_model(8, 26) < 0.31 and root_share_model(4, 26) == 0.25
+    assert 0.28 < root_share_model(8, 26) < 0.31 and root_share_model(4, 26) == root_share_model(8, 26)
+    assert deal_rounds(4, root_share_model(4, 26))[0] == 13 and len(deal_rounds(4, root_share_model(4, 26))[1][0]) == 4
     assert root_share_model(8, 10) == 0.125          # 10 B/position: the gather does not bind, plain cyclic deal
     assert deal_rounds(8, root_share_model(8, 26))[0] == 10 and len(deal_rounds(8, root_share_model(8, 26))[1][0]) == 3
 
