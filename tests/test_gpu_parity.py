@@ -572,6 +572,19 @@ def test_host_chunking_is_bitwise_neutral(mb):
         assert np.array_equal(b.cpu().numpy().reshape(nrows, nx), host[k]), k
 
 
+def test_staged_peer_store_path_is_bitwise_neutral(mb):
+    """The store path k_map takes when its outputs live in ANOTHER GPU's memory (one-byte arrays staged in shared memory
+    and written a 128-byte row segment at a time) is forced onto local outputs and compared byte for byte with the
+    plain stores: row windows starting inside a strip, partial groups of four rows, NULL outputs, a dealt launch, order 2
+    (a 1-GPU box never takes that path otherwise; untouched arrays keep their fill value in both runs)."""
+    import subprocess
+    import sys
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "check_staged_stores.py")], capture_output=True,
+                       text=True, timeout=600)
+    print(p.stdout)
+    assert p.returncode == 0 and "all identical" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
+
+
 def test_output_selection(mb):
     """NULL outputs in the C ABI: unselected arrays are neither stored nor copied; the others are unchanged."""
     s, q, rho, G = 1.0, 0.5, 1e-3, 0.5
